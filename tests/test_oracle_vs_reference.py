@@ -1,0 +1,74 @@
+"""Pin the oracle restatement bit-for-bit against the UNMODIFIED reference executed on
+CPU (oracle.ref_loader).  Skipped where /root/reference does not exist (the GPU box)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from attentionshift_b200.synthetic import structured_scene, vit_state_dict
+from oracle import attnshift as O
+from oracle import ref_loader
+from oracle import vit as V
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+
+
+def _eq(a, b):
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_eq(x, y) for x, y in zip(a, b))
+    if torch.is_tensor(a):
+        return torch.is_tensor(b) and a.shape == b.shape and torch.equal(a, b)
+    return a == b
+
+
+@pytest.mark.parametrize('hp,c,n_obj,seed,noise', [(14, 32, 2, 21, 0.3), (28, 48, 3, 9, 0.4), (20, 40, 5, 4, 0.4)])
+def test_chain_bit_exact(hp, c, n_obj, seed, noise):
+    rh = ref_loader.load_rh()
+    sc = structured_scene(hp, hp, c, n_obj, seed=seed, noise=noise)
+    H = hp * 16
+    up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (H, H), mode='bilinear').reshape(7, n_obj, H, H)
+    self_ = SimpleNamespace()
+    self_.mean_shift_grid_prototype = lambda *a, **k: rh.methods.mean_shift_grid_prototype(self_, *a, **k)
+    torch.manual_seed(seed)
+    r = rh.methods.get_mask_sample_points_roi_best_attn_feat_refine(
+        self_, up, sc['rois'], sc['gt_index'], sc['vit_feat'].clone(), pos_thr=0.6, neg_thr=0.1, num_gt=10,
+        gt_points=sc['gt_points'])
+    torch.manual_seed(seed)
+    o = O.mask_sample_points(up, sc['rois'], sc['gt_index'], sc['vit_feat'].clone(), pos_thr=0.6, neg_thr=0.1,
+                             num_gt=10, gt_points=sc['gt_points'])
+    assert _eq(list(r), list(o))
+    r2 = rh.methods.get_semantic_centers(self_, r[2][-1].clone(), r[3][-1].clone(), sc['rois'], sc['vit_feat'].clone(),
+                                         pos_thr=0.6, refine_times=4, gt_labels=sc['gt_labels'], num_semantic_points=3)
+    o2 = O.semantic_centers(o[2][-1].clone(), o[3][-1].clone(), sc['rois'], sc['vit_feat'].clone(), pos_thr=0.6,
+                            refine_times=4, gt_labels=sc['gt_labels'], num_semantic_points=3)
+    assert _eq(list(r2), list(o2))
+
+
+def test_rollout_and_bbox_bit_exact():
+    rh = ref_loader.load_rh()
+    gen = torch.Generator().manual_seed(0)
+    attns = [torch.softmax(3 * torch.randn(2, 45, 45, generator=gen), -1) for _ in range(7)]
+    assert torch.equal(rh.attns_project_to_feature(attns), O.rollout(attns))
+    sc = structured_scene(14, 14, 16, 2, seed=2)
+    up = F.interpolate(sc['cams_low'].reshape(-1, 1, 14, 14), (224, 224), mode='bilinear').reshape(7, 2, 224, 224)
+    for l in range(7):
+        for i in range(2):
+            rb, rm = rh.get_bbox_from_cam_fast(up[l, i].clone(), sc['gt_points'][i].clone(), cam_thr=0.2,
+                                               area_ratio=0.5, img_size=(224, 224))
+            ob, om = O.bbox_from_cam(up[l, i].clone(), sc['gt_points'][i], 0.2, 0.5, (224, 224))
+            assert torch.equal(rb, ob) and torch.equal(rm, om)
+
+
+def test_vit_block_bit_exact():
+    vt = ref_loader.load_vt()
+    torch.manual_seed(0)
+    blk = vt.Block(dim=128, num_heads=2, mlp_ratio=4, qkv_bias=True,
+                   norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6), return_attention=True).eval()
+    sd = {'b.' + k: v for k, v in blk.state_dict().items()}
+    x = torch.randn(2, 37, 128)
+    with torch.no_grad():
+        ry, ra = blk(x)
+        oy, oa = V.block(x, sd, 'b.', 2)
+    assert torch.equal(ry, oy)
+    assert torch.equal(ra.mean(1), oa)
