@@ -1,0 +1,268 @@
+"""``VisionTransformerDet`` -- drop-in for the reference backbone
+(mmdet/models/backbones/visual_transformer_det.py:60-275, built on models/vision_transformer.py).
+
+Same registry name, constructor kwargs, parameter names (``blocks.{i}.attn.qkv.weight`` ... so MAE
+checkpoints load) and ``forward(x) -> dict`` keys.  The encoder runs on the hand-written sm_100a kernels
+behind the C ABI (tcgen05 GEMMs + flash attention + head-mean pass); torch modules are used only as
+parameter containers and for the small non-hot-path tails (bicubic position-table resize, FPN deconvs,
+point-token MLPs).  Forward-only: attention-shift consumes detached tensors (two_stage_point_align.py:77);
+the attention backward is a later row of the scope table.
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .registry import BACKBONES
+
+
+def trunc_normal_(t, std=.02):
+    return nn.init.trunc_normal_(t, std=std, a=-2., b=2.)
+
+
+class _Mlp(nn.Module):          # parameter container: VT:40-59
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Attention(nn.Module):    # parameter container: VT:62-72
+    def __init__(self, dim, num_heads, qkv_bias):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Block(nn.Module):        # parameter container: VT:88-107
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, eps):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
+        self.attn = _Attention(dim, num_heads, qkv_bias)
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(nn.Module):   # VT:126-139
+    def __init__(self, img_size, patch_size, in_chans, embed_dim):
+        super().__init__()
+        img = img_size[0] if isinstance(img_size, (list, tuple)) else img_size
+        self.num_patches = (img // patch_size) ** 2
+        self.patch_size = patch_size
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+class _PointMLP(nn.Module):     # VTD:26-38
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+        return x
+
+
+@BACKBONES.register_module()
+class VisionTransformerDet(nn.Module):
+    def __init__(self, img_size, patch_size, embed_dim, in_chans=3, with_fpn=True, frozen_stages=-1,
+                 out_indices=[3, 5, 7, 11], use_checkpoint=False, learnable_pos_embed=True, last_feat=False,
+                 recompute_last_feat=False, point_tokens_num=100, num_classes=20, return_attention=False,
+                 with_point_head=True, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=None, init_values=0,
+                 attn_layers=None, **kwargs):
+        super().__init__()
+        assert not with_fpn or (patch_size in (8, 16))
+        assert not recompute_last_feat or (last_feat and recompute_last_feat)
+        if patch_size != 16 or in_chans != 3:
+            raise ValueError('the sm_100a path implements the 16x16 RGB patch embedding used by configs/mae')
+        if embed_dim % num_heads or embed_dim // num_heads != 64:
+            raise ValueError('head_dim must be 64 (ViT-S/B/L)')
+        if drop_rate or attn_drop_rate or drop_path_rate or init_values or qk_scale:
+            raise ValueError('dropout / drop-path / layer-scale / qk_scale are not part of the hot path')
+        self.embed_dim = self.num_features = embed_dim
+        self.num_heads = num_heads
+        self.patch_size = patch_size
+        self.last_feat = last_feat
+        self.recompute_last_feat = recompute_last_feat
+        self.with_fpn = with_fpn
+        self.frozen_stages = frozen_stages
+        self.out_indices = out_indices
+        self.use_checkpoint = use_checkpoint          # accepted for config compatibility (forward-only path)
+        self.return_attention = return_attention
+        self.with_point_head = with_point_head
+        self.point_tokens_num = point_tokens_num
+        # which layers emit their head-mean attention map; None = all (reference behaviour, VTD:236/242).
+        # The attention-shift head only reads the last ``cam_layer`` = 7 (RH:2261): pass attn_layers=7 to skip the rest.
+        self.attn_layers = attn_layers
+
+        self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
+        num_patches = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dim), requires_grad=learnable_pos_embed)
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias, 1e-6) for _ in range(depth)])
+        if with_fpn and patch_size == 16:                 # VTD:106-121
+            self.fpn1 = nn.Sequential(nn.ConvTranspose2d(embed_dim, embed_dim, kernel_size=2, stride=2),
+                                      nn.BatchNorm2d(embed_dim), nn.GELU(),
+                                      nn.ConvTranspose2d(embed_dim, embed_dim, kernel_size=2, stride=2))
+            self.fpn2 = nn.Sequential(nn.ConvTranspose2d(embed_dim, embed_dim, kernel_size=2, stride=2))
+            self.fpn3 = nn.Identity()
+            self.fpn4 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.point_token = nn.Parameter(torch.zeros(1, point_tokens_num, embed_dim))
+        self.point_pos_embed = nn.Parameter(torch.zeros(1, point_tokens_num, embed_dim))
+        if with_point_head:
+            self.class_embed = _PointMLP(embed_dim, embed_dim, num_classes, 3)
+            self.bbox_embed = _PointMLP(embed_dim, embed_dim, 2, 3)
+        trunc_normal_(self.pos_embed)
+        trunc_normal_(self.cls_token)
+        trunc_normal_(self.point_token)
+        trunc_normal_(self.point_pos_embed)
+        self.apply(self._init_weights)
+        self._w16 = {}
+
+    # ---- reference surface -------------------------------------------------
+    def _init_weights(self, m):     # VT:173-185
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def init_weights(self, pretrained=None):    # VTD:179-190
+        if isinstance(pretrained, str):
+            self.apply(self._init_weights)
+            import os
+            if os.path.isfile(pretrained):
+                ckpt = torch.load(pretrained, map_location='cpu')
+                sd = ckpt.get('state_dict', ckpt.get('model', ckpt))
+                self.load_state_dict(sd, strict=False)
+        elif pretrained is None:
+            self.apply(self._init_weights)
+        else:
+            raise TypeError('pretrained must be a str or None')
+
+    def train(self, mode=True):     # VTD:153-156
+        super().train(mode)
+        self._freeze_stages()
+
+    def _freeze_stages(self):       # VTD:158-177
+        if self.frozen_stages >= 0:
+            self.patch_embed.eval()
+            for p in self.patch_embed.parameters():
+                p.requires_grad = False
+            self.cls_token.requires_grad = False
+            self.pos_embed.requires_grad = False
+        for i in range(1, self.frozen_stages + 1):
+            m = self.blocks[i - 1]
+            m.eval()
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    def interpolate_pos_encoding(self, npatch, w, h):   # VT:187-207
+        n0 = self.pos_embed.shape[1] - 1
+        if npatch == n0 and w == h:
+            return self.pos_embed
+        dim = self.pos_embed.shape[-1]
+        w0, h0 = w // self.patch_size + 0.1, h // self.patch_size + 0.1
+        g = int(math.sqrt(n0))
+        pp = F.interpolate(self.pos_embed[:, 1:].reshape(1, g, g, dim).permute(0, 3, 1, 2),
+                           scale_factor=(w0 / math.sqrt(n0), h0 / math.sqrt(n0)), mode='bicubic')
+        assert int(w0) == pp.shape[-2] and int(h0) == pp.shape[-1]
+        pp = pp.permute(0, 2, 3, 1).reshape(1, -1, dim)
+        return torch.cat((self.pos_embed[:, 0].unsqueeze(0), pp), dim=1)
+
+    # ---- device path -------------------------------------------------------
+    def _half(self, name, p, shape=None):
+        """fp16 copy of a weight, refreshed when the parameter is modified in place or replaced."""
+        key = (p.data_ptr(), p._version, p.device)
+        hit = self._w16.get(name)
+        if hit is None or hit[0] != key:
+            w = p.detach()
+            if shape is not None:
+                w = w.reshape(shape)
+            hit = (key, w.to(torch.float16).contiguous())
+            self._w16[name] = hit
+        return hit[1]
+
+    def prepare_tokens(self, img):      # VTD:192-214
+        B, _, w, h = img.shape
+        N = (w // 16) * (h // 16)
+        C = self.embed_dim
+        cols = ops.patch_im2col_f16(img.contiguous().float())
+        emb = ops.linear_f16(cols, self._half('pe', self.patch_embed.proj.weight, (C, 768)),
+                             self.patch_embed.proj.bias.detach().float(), ops.EPI_F32)
+        pos = self.interpolate_pos_encoding(N, w, h).detach()[0].float().contiguous()
+        ptok = (self.point_token + self.point_pos_embed).detach()[0].float().contiguous()
+        return ops.assemble_tokens(emb, self.cls_token.detach().reshape(C).float().contiguous(), pos, ptok, B, N)
+
+    def _block(self, i, x, B, T, want_attn):
+        """VT:109-124 on the device kernels.  x [B*T,C] fp32 (residual stream) -> (x, head-mean attention or None)."""
+        blk = self.blocks[i]
+        h = self.num_heads
+        Tpad = (T + 127) // 128 * 128
+        xn = ops.layernorm_f16(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), blk.norm1.eps)
+        qb = blk.attn.qkv.bias
+        q, k, vt = ops.qkv_proj(xn, self._half(f'qkv{i}', blk.attn.qkv.weight), None if qb is None else qb.detach(),
+                                B, T, h, Tpad)
+        o, m, l = ops.mhsa_fwd(q, k, vt, T)
+        attn = None
+        if want_attn:
+            attn, self._rowsum_part = ops.attn_headmean(q, k, m, l, T)
+        x = ops.linear_f16(o.view(B * T, -1), self._half(f'proj{i}', blk.attn.proj.weight), blk.attn.proj.bias.detach(),
+                           ops.EPI_RESID_F32, resid=x)
+        xn = ops.layernorm_f16(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
+        hid = ops.linear_f16(xn, self._half(f'fc1{i}', blk.mlp.fc1.weight), blk.mlp.fc1.bias.detach(), ops.EPI_GELU_F16)
+        x = ops.linear_f16(hid, self._half(f'fc2{i}', blk.mlp.fc2.weight), blk.mlp.fc2.bias.detach(), ops.EPI_RESID_F32,
+                           resid=x)
+        return x, attn
+
+    @torch.no_grad()
+    def forward(self, x):           # VTD:221-275
+        B, _, H, W = x.shape
+        Hp, Wp = H // self.patch_size, W // self.patch_size
+        tok = self.prepare_tokens(x)
+        T, C = tok.shape[1], tok.shape[2]
+        if self.recompute_last_feat:
+            last_feat = tok
+        xs = tok.view(B * T, C)
+        depth = len(self.blocks)
+        first_attn = 0 if self.attn_layers is None else depth - int(self.attn_layers)
+        features, attns = [], []
+        Tp = self.point_tokens_num
+        for i in range(depth):
+            want = self.return_attention and i >= first_attn
+            xs, a = self._block(i, xs, B, T, want)
+            if self.return_attention:
+                attns.append(a)
+            if i in self.out_indices:
+                xp = xs.view(B, T, C)[:, 1:, :][:, :-Tp].permute(0, 2, 1).reshape(B, -1, Hp, Wp)
+                features.append(xp.contiguous())
+            if self.last_feat and (not self.recompute_last_feat) and i == depth - 1:
+                last_feat = xs.view(B, T, C)[:, :-Tp]
+        xo = xs.view(B, T, C)
+        org_features = torch.stack(features, dim=1)
+        if self.with_fpn:
+            fops = [self.fpn1, self.fpn2, self.fpn3, self.fpn4]
+            for i in range(len(features)):
+                features[i] = fops[i](features[i])
+        point_tokens = xo[:, -Tp:]
+        ret = dict(org_feats=org_features, feature=tuple(features), point_tokens=point_tokens)
+        if self.with_point_head:
+            ret.update(dict(outputs_class=self.class_embed(point_tokens),
+                            outputs_coord=self.bbox_embed(point_tokens).sigmoid()))
+        if self.return_attention and self.last_feat:
+            ret.update(dict(attns=attns))
+        if self.last_feat:
+            ret.update(dict(last_feat=last_feat))
+        return ret

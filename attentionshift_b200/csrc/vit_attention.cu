@@ -1,0 +1,414 @@
+// Multi-head self-attention core of the ViT block on tcgen05 / TMEM, fed by TMA.
+// Reference ops replaced (models/vision_transformer.py): :79 q @ k^T * scale, :80 softmax, :83 attn @ v,
+// and visual_transformer_det.py:236/242 attn.mean(1) (the head-mean probabilities every layer hands to the
+// attention-shift head).  The [B,h,T,T] probability tensor (845 MB / image / layer at 1024^2) is never materialised.
+//
+// as_mhsa_fwd      : flash-style forward. One CTA = one (batch, head, 128-query tile); 2 CTAs co-reside per SM.
+//                    warp 0 TMA producer (Q once, K / V^T tiles through a 2-stage ring), warp 1 tcgen05.mma issuer
+//                    (S = Q K^T into TMEM, O += P V with P read from TMEM), warps 2..5 one softmax thread per query row
+//                    (tcgen05.ld S, online max / exp2 / sum, fp16 P back into TMEM, O rescale in TMEM).
+//                    Outputs O [B,T,C] fp16 and the per-row log2-domain max m and denominator l [B,h,T].
+// as_attn_headmean : second pass for layers whose attention map is consumed: for a (128 x 128) tile loops the heads,
+//                    recomputes S_h on tensor cores and accumulates exp2(S_h*c - m_h) / l_h in registers; writes the
+//                    head-mean tile once (+ deterministic row-sum partials for the roll-out normaliser).
+#include "common.cuh"
+#include <math.h>
+
+using namespace asb;
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int TILE_BYTES = BQ * HD * 2;   // 16 KB: 128 rows x 128 B (also one K tile, also one V^T tile = 2 x (64 x 128 B))
+
+// ------------------------------------------------------------------ forward
+constexpr int FWD_THREADS = 192;
+constexpr int FWD_SMEM = 5 * TILE_BYTES + 1024 + 256;
+constexpr uint32_t COL_S = 0, COL_O = 128, COL_P = 192;
+
+struct FwdParams {
+  int T, heads, nkv;
+  float scale_log2;     // head_dim^-0.5 * log2(e)
+  __half* o;            // [B, T, heads*64]
+  float* m;             // [B, heads, T]
+  float* l;             // [B, heads, T]
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = smem + TILE_BYTES;          // 2 stages
+  uint8_t* v_s = smem + 3 * TILE_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // 2
+  uint64_t* kv_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(q_s, &tm_q, q_full, 0, qt * BQ, bh);
+      for (int j = 0; j < p.nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_3d(k_s + st * TILE_BYTES, &tm_k, &kv_full[st], 0, j * BKV, bh);
+        tma_load_3d(v_s + st * TILE_BYTES, &tm_v, &kv_full[st], j * BKV, 0, bh);
+        tma_load_3d(v_s + st * TILE_BYTES + TILE_BYTES / 2, &tm_v, &kv_full[st], j * BKV + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
+    constexpr uint32_t idesc_o = umma_idesc(0, BQ, HD);
+    mbar_wait(q_full, 0);
+    const uint32_t q_base = smem_u32(q_s);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t k_base = smem_u32(k_s + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + COL_S, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < p.nkv; ++j) {
+      const int st = j & 1;
+      if (j + 1 < p.nkv) issue_s(j + 1);    // S_{j+1} runs on the tensor pipe while the softmax warps finish tile j
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_base = smem_u32(v_s + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          mma_f16_ts(tmem + COL_O, tmem + COL_P + k * 8,
+                     umma_desc_k_sw128(v_base + (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32), idesc_o, (j | k) != 0);
+        tc_commit(&kv_empty[st]);
+        tc_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int t = qt * BQ + row;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < p.nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv0 = j * BKV;
+      const bool tail = kv0 + BKV > p.T;
+      // pass 1: row maximum of the scaled logits
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + COL_S + c * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (tail && kv0 + c * 32 + i >= p.T) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = ex2_approx(m_run - m_new);       // 0 on the first tile (m_run = -inf)
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);            // P buffer and O accumulator are free again
+      tc_fence_after();
+      // pass 2: p = exp2(s*c - m), packed fp16 into the P columns
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + COL_S + c * 32, v);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+          float p0 = ex2_approx(fmaf(s0, p.scale_log2, -m_new));
+          float p1 = ex2_approx(fmaf(s1, p.scale_log2, -m_new));
+          if (tail) {
+            if (kv0 + c * 32 + 2 * i >= p.T) p0 = 0.f;
+            if (kv0 + c * 32 + 2 * i + 1 >= p.T) p1 = 0.f;
+          }
+          sum += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        tmem_st_32x16(lane_addr + COL_P + c * 16, pk);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);                  // S fully read: the next Q K^T may overwrite it
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (j > 0) {                                          // rescale the running output
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + COL_O + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32(lane_addr + COL_O + c * 32, v);
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (p.nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const bool live = t < p.T;
+    __half* dst = p.o + ((size_t)b * p.T + (live ? t : 0)) * (p.heads * HD) + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(lane_addr + COL_O + c * 32, v);   // .sync.aligned: executed by every lane, stores are predicated
+      tc_wait_ld();
+      if (live) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half2 hh = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * e]) * inv_l, __uint_as_float(v[8 * i + 2 * e + 1]) * inv_l);
+            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          d4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (live) {
+      p.m[(size_t)bh * p.T + t] = m_run;
+      p.l[(size_t)bh * p.T + t] = l_run;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------ head-mean probabilities
+constexpr int HM_THREADS = 192;
+constexpr int HM_SMEM_TILES = 4 * TILE_BYTES;               // 2 stages x (Q_h, K_h)
+constexpr int HM_STAGE_LD = 129;                            // floats per staged output row (padded: conflict-free)
+constexpr int HM_SMEM = HM_SMEM_TILES + 1024 + 256 + BQ * HM_STAGE_LD * 4;
+
+struct HmParams {
+  int T, heads, ld;           // ld = row stride (floats) of the output
+  float scale_log2;
+  const float* m;             // [B, heads, T]
+  const float* l;
+  float* out;                 // [B, T, ld]
+  float* rowsum_part;         // [B, T, ntile] or null
+  int ntile;
+};
+
+__global__ void __launch_bounds__(HM_THREADS, 1)
+attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const HmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HM_SMEM_TILES);
+  uint64_t* full = bars;        // 2
+  uint64_t* empty = bars + 2;   // 2
+  uint64_t* s_full = bars + 4;  // 2
+  uint64_t* s_empty = bars + 6; // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int h = 0; h < p.heads; ++h) {
+        const int st = h & 1;
+        mbar_wait(&empty[st], ((h >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], 2 * TILE_BYTES);
+        tma_load_3d(smem + (2 * st) * TILE_BYTES, &tm_q, &full[st], 0, qt * BQ, b * p.heads + h);
+        tma_load_3d(smem + (2 * st + 1) * TILE_BYTES, &tm_k, &full[st], 0, kt * BKV, b * p.heads + h);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
+    for (int h = 0; h < p.heads; ++h) {
+      const int st = h & 1;
+      mbar_wait(&full[st], (h >> 1) & 1);
+      mbar_wait(&s_empty[st], ((h >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t q_base = smem_u32(smem + (2 * st) * TILE_BYTES), k_base = smem_u32(smem + (2 * st + 1) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + st * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
+        tc_commit(&empty[st]);
+        tc_commit(&s_full[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int t = qt * BQ + row;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+    for (int h = 0; h < p.heads; ++h) {
+      const int st = h & 1;
+      float mrow = 0.f, inv_l = 0.f;      // rows >= T contribute exactly 0
+      if (t < p.T) {
+        const size_t si = ((size_t)b * p.heads + h) * p.T + t;
+        mrow = p.m[si];
+        inv_l = 1.f / p.l[si];
+      }
+      mbar_wait(&s_full[st], (h >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + st * 128 + c * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          acc[c * 32 + i] = fmaf(exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mrow)), inv_l, acc[c * 32 + i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+    }
+    // stage through smem so the global stores are row-contiguous
+    float* stage = reinterpret_cast<float*>(smem + HM_SMEM_TILES + 256);
+    const float inv_h = 1.f / (float)p.heads;
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // all 4 epilogue warps are past their last MMA-visible smem use
+    float rs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) {
+      const float v = (kt * BKV + i < p.T) ? acc[i] * inv_h : 0.f;
+      rs += v;
+      stage[row * HM_STAGE_LD + i] = v;
+    }
+    if (p.rowsum_part && t < p.T) p.rowsum_part[((size_t)b * p.T + t) * p.ntile + kt] = rs;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int ncol = min(BKV, p.T - kt * BKV);
+    for (int r = (warp - 2); r < BQ; r += 4) {
+      const int tr = qt * BQ + r;
+      if (tr >= p.T) break;
+      float* dst = p.out + ((size_t)b * p.T + tr) * p.ld + kt * BKV;
+      for (int c = lane; c < ncol; c += 32) dst[c] = stage[r * HM_STAGE_LD + c];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+int encode_qk(CUtensorMap* tm, const void* base, int BH, int T) {
+  uint64_t dims[3] = {HD, (uint64_t)T, (uint64_t)BH};
+  uint64_t str[2] = {HD * 2, (uint64_t)T * HD * 2};
+  uint32_t box[3] = {HD, BQ, 1};
+  return as_encode_tmap(tm, base, 2, 3, dims, str, box);
+}
+
+}  // namespace
+
+extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T,
+                           int Tpad, int heads, cudaStream_t stream) {
+  if (Tpad % BKV || Tpad < T) return AS_ERR_BAD_ARG;
+  CUtensorMap tm_q, tm_k, tm_v;
+  int r = encode_qk(&tm_q, q, B * heads, T);
+  if (r) return r;
+  r = encode_qk(&tm_k, k, B * heads, T);
+  if (r) return r;
+  uint64_t dims[3] = {(uint64_t)Tpad, HD, (uint64_t)B * heads};
+  uint64_t str[2] = {(uint64_t)Tpad * 2, (uint64_t)Tpad * HD * 2};
+  uint32_t box[3] = {64, HD, 1};
+  r = as_encode_tmap(&tm_v, vt, 2, 3, dims, str, box);
+  if (r) return r;
+  static bool attr = false;
+  if (!attr) {
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
+  FwdParams p;
+  p.T = T; p.heads = heads; p.nkv = (T + BKV - 1) / BKV;
+  p.scale_log2 = (float)(0.125 * 1.4426950408889634);   // head_dim^-0.5 (VT:67), head_dim = 64
+  p.o = (__half*)o; p.m = m; p.l = l;
+  mhsa_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), FWD_THREADS, FWD_SMEM, stream>>>(tm_q, tm_k, tm_v, p);
+  AS_LAUNCH_CHECK();
+  return 0;
+}
+
+// out [B,T,ld] fp32 (ld >= T), rowsum_part [B,T,ceil(T/128)] (may be null)
+extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
+                                float* rowsum_part, int B, int T, int heads, cudaStream_t stream) {
+  if (ld < T) return AS_ERR_BAD_ARG;
+  CUtensorMap tm_q, tm_k;
+  int r = encode_qk(&tm_q, q, B * heads, T);
+  if (r) return r;
+  r = encode_qk(&tm_k, k, B * heads, T);
+  if (r) return r;
+  static bool attr = false;
+  if (!attr) {
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
+    attr = true;
+  }
+  HmParams p;
+  p.T = T; p.heads = heads; p.ld = ld; p.scale_log2 = (float)(0.125 * 1.4426950408889634);
+  p.m = m; p.l = l; p.out = out; p.rowsum_part = rowsum_part; p.ntile = (T + BKV - 1) / BKV;
+  const int nt = (T + BQ - 1) / BQ;
+  attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
+  AS_LAUNCH_CHECK();
+  return 0;
+}

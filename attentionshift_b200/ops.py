@@ -1,0 +1,134 @@
+"""Thin tensor-level wrappers over the C ABI (one python function per exported kernel family).
+
+Every function takes/returns CUDA tensors, launches on the current stream and never
+synchronises.  Shapes follow the reference (RH = stdroi_point_deform_attn_reppoints.py,
+VT = models/vision_transformer.py)."""
+import torch
+
+from . import lib as _l
+
+EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 4
+
+
+def linear_f16(x, w, bias=None, mode=EPI_F16, resid=None):
+    """y = x @ w.T (+bias) on tcgen05 tensor cores.  x [M,K] fp16, w [N,K] fp16, bias [N] fp32.
+    mode: EPI_F16 -> fp16, EPI_GELU_F16 -> gelu -> fp16, EPI_RESID_F32 -> fp32 resid + y, EPI_F32 -> fp32."""
+    L = _l.load()
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and w.shape[1] == K
+    out = torch.empty(M, N, device=x.device, dtype=torch.float16 if mode in (EPI_F16, EPI_GELU_F16) else torch.float32)
+    _l.check(L.as_linear_f16(_l.ptr(x), _l.ptr(w), _l.ptr(bias), _l.ptr(out), _l.ptr(resid), M, N, K, mode,
+                             _l.stream_ptr()), 'as_linear_f16')
+    return out
+
+
+def qkv_proj(x, w, bias, B, T, heads, Tpad):
+    """VT:76 qkv Linear + head split.  x [B*T,C] fp16 -> q,k [B,h,T,64] fp16, vT [B,h,64,Tpad] fp16 (zero padded)."""
+    L = _l.load()
+    q = torch.empty(B, heads, T, 64, device=x.device, dtype=torch.float16)
+    k = torch.empty_like(q)
+    vt = torch.zeros(B, heads, 64, Tpad, device=x.device, dtype=torch.float16)
+    _l.check(L.as_qkv_proj_f16(_l.ptr(x), _l.ptr(w), _l.ptr(bias), _l.ptr(q), _l.ptr(k), _l.ptr(vt), B, T, Tpad, heads,
+                               _l.stream_ptr()), 'as_qkv_proj_f16')
+    return q, k, vt
+
+
+def layernorm_f16(x, gamma, beta, eps=1e-6):
+    """VT:110/114 LayerNorm (eps 1e-6, VT:146) fused with the fp16 cast of the next GEMM operand.  x [M,C] fp32."""
+    L = _l.load()
+    M, C = x.shape
+    y = torch.empty(M, C, device=x.device, dtype=torch.float16)
+    _l.check(L.as_layernorm_f16(_l.ptr(x), _l.ptr(gamma), _l.ptr(beta), _l.ptr(y), M, C, float(eps), _l.stream_ptr()),
+             'as_layernorm_f16')
+    return y
+
+
+def patch_im2col_f16(img):
+    """img [B,3,H,W] fp32 -> [B*hp*wp, 768] fp16 patch rows (the 16x16/16 conv of VT:136 becomes a GEMM)."""
+    L = _l.load()
+    B, _, H, W = img.shape
+    cols = torch.empty(B * (H // 16) * (W // 16), 768, device=img.device, dtype=torch.float16)
+    _l.check(L.as_patch_im2col_f16(_l.ptr(img), _l.ptr(cols), B, H, W, _l.stream_ptr()), 'as_patch_im2col_f16')
+    return cols
+
+
+def assemble_tokens(emb, cls, pos, ptok, B, N):
+    """VTD:203-213: [cls+pos0 | patches+pos | point tokens].  emb [B*N,C], cls [C], pos [1+N,C], ptok [Tp,C] -> [B,T,C]."""
+    L = _l.load()
+    C = emb.shape[1]
+    Tp = ptok.shape[0]
+    x = torch.empty(B, 1 + N + Tp, C, device=emb.device, dtype=torch.float32)
+    _l.check(L.as_assemble_tokens(_l.ptr(emb), _l.ptr(cls), _l.ptr(pos), _l.ptr(ptok), _l.ptr(x), B, N, Tp, C,
+                                  _l.stream_ptr()), 'as_assemble_tokens')
+    return x
+
+
+def mhsa_fwd(q, k, vt, T):
+    """VT:79-83 without materialising attn.  q,k [B,h,T,64], vt [B,h,64,Tpad] fp16
+    -> (o [B,T,h*64] fp16, m [B,h,T], l [B,h,T] fp32 softmax row statistics, log2 domain)."""
+    L = _l.load()
+    B, heads = q.shape[0], q.shape[1]
+    Tpad = vt.shape[3]
+    o = torch.empty(B, T, heads * 64, device=q.device, dtype=torch.float16)
+    m = torch.empty(B, heads, T, device=q.device, dtype=torch.float32)
+    l = torch.empty_like(m)
+    _l.check(L.as_mhsa_fwd(_l.ptr(q), _l.ptr(k), _l.ptr(vt), _l.ptr(o), _l.ptr(m), _l.ptr(l), B, T, Tpad, heads,
+                           _l.stream_ptr()), 'as_mhsa_fwd')
+    return o, m, l
+
+
+def attn_headmean(q, k, m, l, T, want_rowsum=True):
+    """VTD:236/242 attn.mean(1) recomputed from (q, k, m, l).  -> (mean [B,T,T] view of a row-padded buffer,
+    rowsum partials [B,T,ceil(T/128)] or None)."""
+    L = _l.load()
+    B, heads = q.shape[0], q.shape[1]
+    ld = (T + 127) // 128 * 128
+    buf = torch.empty(B, T, ld, device=q.device, dtype=torch.float32)
+    nt = (T + 127) // 128
+    part = torch.empty(B, T, nt, device=q.device, dtype=torch.float32) if want_rowsum else None
+    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), B, T, heads,
+                                _l.stream_ptr()), 'as_attn_headmean')
+    return buf[:, :, :T], part
+
+
+def _feat_args(feats):
+    """feats [n_img, N, C] fp32, last two dims contiguous (image stride free)."""
+    assert feats.dtype == torch.float32 and feats.stride(2) == 1 and feats.stride(1) == feats.shape[2]
+    return feats.stride(0)
+
+
+def grid_seeds(maps, feats, obj_img, rois, wp, S, thr=0.35):
+    """RH:1786-1810.  maps [n_tot,N] fp32, feats [n_img,N,C], obj_img [n_tot] int32, rois [n_tot,4] fp32.
+    -> (seed token ids [n_tot,S] int32, prototypes [n_tot,S,C] fp32)."""
+    L = _l.load()
+    n_tot, N = maps.shape
+    C = feats.shape[2]
+    tok = torch.empty(n_tot, S, device=maps.device, dtype=torch.int32)
+    proto = torch.empty(n_tot, S, C, device=maps.device, dtype=torch.float32)
+    _l.check(L.as_grid_seeds(_l.ptr(maps), float(thr), ctypes_ptr(feats), _feat_args(feats), _l.ptr(obj_img), _l.ptr(rois),
+                             n_tot, N, C, wp, S, _l.ptr(tok), _l.ptr(proto), _l.stream_ptr()), 'as_grid_seeds')
+    return tok, proto
+
+
+def ctypes_ptr(t):
+    import ctypes
+    assert t.is_cuda
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True, want_trace=False):
+    """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C].
+    -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None)."""
+    L = _l.load()
+    n_tot, S, C = proto.shape
+    n_img, N, _ = feats.shape
+    proto = proto.contiguous().clone()
+    sim = torch.empty(n_tot, S, N, device=proto.device, dtype=torch.float32)
+    trace = torch.empty(n_shift, n_tot, N, device=proto.device, dtype=torch.int32) if want_trace else None
+    nbytes = L.as_mean_shift_workspace(n_img, n_tot, S, N, C)
+    ws = torch.empty(nbytes, device=proto.device, dtype=torch.uint8)
+    _l.check(L.as_mean_shift(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(obj_img), _l.ptr(rois),
+                             n_tot, S, _l.ptr(proto), _l.ptr(sim), n_shift, float(tau), float(temp), int(clamp0),
+                             _l.ptr(trace), _l.ptr(ws), nbytes, _l.stream_ptr()), 'as_mean_shift')
+    return proto, sim, trace

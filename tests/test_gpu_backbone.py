@@ -1,0 +1,56 @@
+"""VisionTransformerDet on the device kernels vs (a) the golden vectors produced by the UNMODIFIED reference class and
+(b) the CPU oracle at ViT-B width.  Tolerances: the reference's own GPU path is fp16 GEMM + fp32 softmax (apex O1);
+we use fp16 operands with fp32 accumulation, so last_feat agrees to ~1e-3 of its scale and the head-mean attention
+maps to <= 1e-3 relative (north_star)."""
+import os
+
+import pytest
+import torch
+
+from attentionshift_b200.synthetic import vit_state_dict
+from oracle import vit as V
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(embed, heads, depth, img, n_pt, sd):
+    from attentionshift_b200.registry import build_backbone
+    m = build_backbone(dict(type='VisionTransformerDet', img_size=img, patch_size=16, embed_dim=embed, depth=depth,
+                            num_heads=heads, mlp_ratio=4, qkv_bias=True, with_fpn=False, last_feat=True,
+                            return_attention=True, point_tokens_num=n_pt, with_point_head=False,
+                            out_indices=[depth - 1]))
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return m.cuda().eval()
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def test_backbone_vs_reference_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, 'vit_e128_d2.pt'))
+    m_ = g['meta']
+    sd = vit_state_dict(m_['embed'], m_['depth'], m_['heads'], m_['img'], n_point_tokens=m_['n_pt'], seed=m_['seed'])
+    model = _build(m_['embed'], m_['heads'], m_['depth'], m_['img'], m_['n_pt'], sd)
+    gen = torch.Generator().manual_seed(m_['seed'] + 1)
+    x = torch.randn(2, 3, m_['img'], m_['img'], generator=gen)
+    out = model(x.cuda())
+    assert set(out) >= {'org_feats', 'feature', 'point_tokens', 'attns', 'last_feat'}
+    for a, b in zip(out['attns'], g['attns']):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-3, atol=2e-6)
+    assert _rel(out['last_feat'].cpu(), g['last_feat']) < 2e-3
+    assert _rel(out['point_tokens'].cpu(), g['point_tokens']) < 2e-3
+
+
+@pytest.mark.parametrize('embed,heads,depth,img', [(768, 12, 2, 224), (384, 6, 3, 160)])
+def test_backbone_vs_oracle(embed, heads, depth, img):
+    sd = vit_state_dict(embed, depth, heads, img, seed=3)
+    model = _build(embed, heads, depth, img, 100, sd)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 3, img, img, generator=gen)
+    out = model(x.cuda())
+    ref = V.backbone_forward(x, sd, depth, heads)
+    for a, b in zip(out['attns'], ref['attns']):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-3, atol=2e-6)
+    assert _rel(out['last_feat'].cpu(), ref['last_feat']) < 2e-3
