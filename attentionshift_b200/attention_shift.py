@@ -1,0 +1,411 @@
+"""Attention shift on the device: roll-out slab -> CAM boxes -> refined instance maps -> mask points ->
+mean-shift part discovery -> pseudo masks.  Host orchestration of the C-ABI kernels for the body of
+``seed_pseudo_gt`` (RH = mmdet/models/roi_heads/stdroi_point_deform_attn_reppoints.py, RH:2261-2361).
+
+Instances of the whole batch are a flat list (``obj_img`` maps instance -> image), every stage is batched over it.
+The reference synchronises with the host for every instance / component / seed map (``unique()``, ``.tolist()``,
+``nonzero()``, python loops); here the host is consulted exactly three times per batch:
+  (1) candidate counts for the random seed points   (the RNG is torch's CPU generator, like the reference),
+  (2) candidate counts for the mask-head points,
+  (3) the final part counts / validity flags needed to build the ragged python lists of the return dict.
+
+RNG discipline: kernels take the drawn indices as inputs.  ``StreamRng`` replays the reference's
+call sequence on one generator (exact stream parity; needs one image per call and a full ``randperm``);
+``KeyedRng`` keys one generator per (image, stage, instance) so a batch needs no per-image ordering and
+``randperm(n)[:k]`` is evaluated from its first k draws only.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _l
+from . import ops
+
+PATCH = 16
+
+
+# --------------------------------------------------------------------------------------------------- RNG front ends
+class StreamRng:
+    """The reference's own call sequence on a single torch CPU generator (default: the global one)."""
+
+    def __init__(self, generator=None):
+        self.g = generator
+
+    def randint(self, key, high, n):
+        return torch.randint(high, (n,), generator=self.g)
+
+    def randperm_head(self, key, n, k):
+        return torch.randperm(n, generator=self.g)[:k]
+
+
+class KeyedRng:
+    """One torch CPU generator per (image, stage, instance) key.  Same algorithms as torch.randint / torch.randperm
+    (mt19937, ``random() % range``, forward Fisher-Yates) so a reference run seeded with ``seed_for(key)`` right before
+    the corresponding call yields identical indices."""
+
+    def __init__(self, base_seed=0):
+        self.base = int(base_seed)
+
+    def seed_for(self, key):
+        img, stage, obj = key
+        return (self.base * 1000003 + img * 10007 + stage * 101 + obj) & 0x7fffffff
+
+    def _gen(self, key):
+        return torch.Generator().manual_seed(self.seed_for(key))
+
+    def randint(self, key, high, n):
+        return torch.randint(high, (n,), generator=self._gen(key))
+
+    def randperm_head(self, key, n, k):
+        if n <= 4096:
+            return torch.randperm(n, generator=self._gen(key))[:k]
+        # the first k outputs of torch's CPU randperm (forward Fisher-Yates, TensorFactories.cpp) depend only on its
+        # first k draws z_i = random() % (n - i), which is exactly what torch.randint(n - i, (1,)) consumes
+        g = self._gen(key)
+        perm, out = {}, []
+        for i in range(min(k, n - 1)):
+            j = i + int(torch.randint(n - i, (1,), generator=g))
+            vi, vj = perm.get(i, i), perm.get(j, j)
+            perm[i], perm[j] = vj, vi
+            out.append(vj)
+        return torch.tensor(out, dtype=torch.int64)
+
+
+def _fill_index(idx, n):
+    """RH:1147-1155 ``fill_in_idx`` on a 1-D index tensor."""
+    assert idx.shape[0] != 0
+    if idx.shape[0] >= n / 2:
+        return torch.cat((idx, idx[:n - idx.shape[0]]), dim=0)
+    return _fill_index(idx.repeat(n // idx.shape[0]), n)
+
+
+def _i32(x, dev):
+    return torch.as_tensor(x, dtype=torch.int32).to(dev, non_blocking=True)
+
+
+def _f32(x, dev):
+    return torch.as_tensor(x, dtype=torch.float32).to(dev, non_blocking=True)
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 1), device=dev, dtype=torch.uint8)
+
+
+def _sp():
+    return _l.stream_ptr()
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def token_major(vit_feat):
+    """[B,C,Hp,Wp] (the reference hands over a permuted view of last_feat, DET:77) or [B,N,C] -> [B,N,C] fp32 with
+    unit channel stride, without a copy when the memory already is token-major."""
+    if vit_feat.dim() == 4:
+        b, c, hp, wp = vit_feat.shape
+        t = vit_feat.permute(0, 2, 3, 1).reshape(b, hp * wp, c)
+    else:
+        t = vit_feat
+    if t.dtype != torch.float32 or t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+        t = t.float().contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------------------------------- A5: roll-out
+def rollout_rows(attns, n_rows):
+    """RH:1257-1272 restricted to the last ``n_rows`` rows.  attns: list of L tensors [B,T,T] (row stride may be padded).
+    -> [B, L, n_rows, T] (index 0 = last layer alone)."""
+    L = _l.load()
+    nl = len(attns)
+    B, T, _ = attns[0].shape
+    ld = attns[0].stride(1)
+    dev = attns[0].device
+    parts = []
+    for a in attns:
+        assert a.dtype == torch.float32 and a.stride(2) == 1 and a.stride(1) == ld and a.stride(0) == T * ld
+        p = getattr(a, '_as_rowsum_part', None)
+        parts.append(p if p is not None else a.sum(-1, keepdim=True).contiguous())
+    ntile = parts[0].shape[2]
+    out = torch.empty(B, nl, n_rows, T, device=dev, dtype=torch.float32)
+    a_ptrs = (ctypes.c_void_p * nl)(*[a.data_ptr() for a in attns])
+    p_ptrs = (ctypes.c_void_p * nl)(*[p.data_ptr() for p in parts])
+    nbytes = L.as_rollout_workspace(B, T, n_rows)
+    ws = _ws(nbytes, dev)
+    _l.check(L.as_rollout_rows(a_ptrs, p_ptrs, nl, B, T, ld, ntile, n_rows, _p(out), _p(ws), nbytes, _sp()), 'as_rollout_rows')
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- A6 / A7
+def cam_boxes(rows, obj_img, obj_pt, gt_points, hp, wp, cam_thr=0.2, area_ratio=0.5, want_keep_mask=False):
+    """RH:2272-2290: slice the matched point-token rows, (virtual) x16 bilinear, get_bbox_from_cam_fast per (layer, gt).
+    rows [B,L,n_rows,T]; obj_img/obj_pt int32 [n_tot]; gt_points [n_tot,2] (x,y).
+    -> (cams [L,n_tot,N] low-res, minmax [L,n_tot,2], boxes [L,n_tot,4], keep_mask or None)."""
+    L = _l.load()
+    B, nl, n_rows, T = rows.shape
+    n_tot = obj_img.shape[0]
+    N = hp * wp
+    dev = rows.device
+    cams = torch.empty(nl, n_tot, N, device=dev, dtype=torch.float32)
+    _l.check(L.as_cam_gather(_p(rows), _p(obj_img), _p(obj_pt), nl, n_rows, T, N, n_tot, _p(cams), _sp()), 'as_cam_gather')
+    n_maps = nl * n_tot
+    mm = torch.empty(n_maps, 2, device=dev, dtype=torch.float32)
+    scratch = torch.empty(n_maps * 2, device=dev, dtype=torch.int32)
+    _l.check(L.as_cam_minmax(_p(cams), n_maps, hp, wp, _p(mm), _p(scratch), _sp()), 'as_cam_minmax')
+    boxes = torch.empty(n_maps, 4, device=dev, dtype=torch.float32)
+    keep = torch.empty(n_maps, hp * 16, wp * 16, device=dev, dtype=torch.uint8) if want_keep_mask else None
+    nbytes = L.as_cam_bbox_workspace(n_maps, hp * 16, wp * 16)
+    ws = _ws(nbytes, dev)
+    _l.check(L.as_cam_bbox(_p(cams), _p(mm), _p(gt_points), n_maps, n_tot, hp, wp, float(cam_thr), float(area_ratio),
+                           _p(boxes), _p(keep), _p(ws), nbytes, _sp()), 'as_cam_bbox')
+    return cams, mm.view(nl, n_tot, 2), boxes.view(nl, n_tot, 4), keep
+
+
+def cosine_maps(feats, grp_img, protos, clamp0=False):
+    """sim[g,s,n] = cos(protos[g,s], feats[grp_img[g],n]).  feats [n_img,N,C], protos [G,S,C] -> [G,S,N]."""
+    L = _l.load()
+    n_img, N, C = feats.shape
+    G, S, _ = protos.shape
+    sim = torch.empty(G, S, N, device=feats.device, dtype=torch.float32)
+    nbytes = L.as_cosine_maps_workspace(n_img, G, S, N, C)
+    ws = _ws(nbytes, feats.device)
+    _l.check(L.as_cosine_maps(_p(feats), feats.stride(0), n_img, N, C, _p(grp_img), _p(protos), G, S, _p(sim), int(clamp0),
+                              _p(ws), nbytes, _sp()), 'as_cosine_maps')
+    return sim
+
+
+# --------------------------------------------------------------------------------------------------- A8
+class _Groups:
+    """Row layout of the refinement state: per image g, rows [0,n) fg instances, row n the image-level bg supplement,
+    rows (n, 2n] bg instances; padded to S = max(2n+1)."""
+
+    def __init__(self, n_per_img, dev):
+        self.n = list(n_per_img)
+        self.first = [0]
+        for k in self.n[:-1]:
+            self.first.append(self.first[-1] + k)
+        self.S = max(2 * k + 1 for k in self.n)
+        self.G = len(self.n)
+        self.d_first = _i32(self.first, dev)
+        self.d_n = _i32(self.n, dev)
+        self.d_img = torch.arange(self.G, dtype=torch.int32, device=dev)
+
+
+def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng, thr_pos=0.2, thr_neg=0.1,
+                 num_points=20, refine_times=2, obj_tau=0.85, mask_thr=0.6, want_bg=True, want_mask=True):
+    """RH:1000-1019 for every instance of the batch.
+    cam_low [n_tot,N] / cam_mm [n_tot,2]: selected-layer CAM (low-res) and min/max of its up-sampling; feats [n_img,N,C];
+    rois [n_tot,4]; gt_points [n_tot,2].  -> dict(map_fg, map_bg [n_tot,H,W], mask uint8, fg_low, bg_low [n_tot,N],
+    fg_feat [G,S,C] (rows 0..n of each group), pts [G,S,P,2], groups)."""
+    L = _l.load()
+    dev = feats.device
+    n_img, N, C = feats.shape
+    n_tot = cam_low.shape[0]
+    H, W = hp * PATCH, wp * PATCH
+    grp = _Groups(n_per_img, dev)
+    P = num_points
+    # ---- candidate counts: items ordered per image as the reference draws them: bg instances, fg instances, supplement
+    kinds, ia, ib, thr, item_img, item_slot = [], [], [], [], [], []
+    for g, n in enumerate(grp.n):
+        o0 = grp.first[g]
+        for j in range(n):
+            kinds.append(0); ia.append(o0 + j); ib.append(0); thr.append(thr_neg); item_img.append(g); item_slot.append(n + 1 + j)
+        for j in range(n):
+            kinds.append(1); ia.append(o0 + j); ib.append(0); thr.append(thr_pos); item_img.append(g); item_slot.append(j)
+        kinds.append(2); ia.append(o0); ib.append(o0 + n); thr.append(thr_neg); item_img.append(g); item_slot.append(n)
+    n_items = len(kinds)
+    d_kind, d_a, d_b = _i32(kinds, dev), _i32(ia, dev), _i32(ib, dev)
+
+    def count(thr_list):
+        d_thr = _f32(thr_list, dev)
+        rc = torch.empty(n_items, H, device=dev, dtype=torch.int32)
+        _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), n_items, hp, wp, _p(rc),
+                                    _sp()), 'as_norm_rowcount')
+        return rc, d_thr, rc.sum(1).cpu().tolist()           # host sync (1)
+
+    rowcnt, d_thr, totals = count(thr)
+    # bg candidates too few -> the reference doubles the threshold until there are enough (RH:360-364)
+    factor = [1.0] * n_items
+    while any(kinds[i] != 1 and totals[i] < P for i in range(n_items)):
+        for i in range(n_items):
+            if kinds[i] != 1 and totals[i] < P:
+                factor[i] *= 2
+        rowcnt, d_thr, totals = count([t * f for t, f in zip(thr, factor)])
+    sel_item, sel_k, sel_dst = [], [], []
+    pts_host = torch.zeros(grp.G, grp.S, P, 2, dtype=torch.int32)
+    gtp = gt_points.detach().cpu()
+    for i in range(n_items):
+        g, slot, num = item_img[i], item_slot[i], totals[i]
+        key = (g, 0, slot)
+        if kinds[i] == 1 and num < P:                        # RH:354-358: all candidates, then the GT point repeated
+            ks = list(range(num))
+            pts_host[g, slot, num:, 0] = int(gtp[ia[i], 0])
+            pts_host[g, slot, num:, 1] = int(gtp[ia[i], 1])
+        else:
+            step = num // P
+            n_draw = len(range(0, num, step))
+            ks = (rng.randint(key, num, n_draw) % num)[:P].tolist()
+        for j, k in enumerate(ks):
+            sel_item.append(i); sel_k.append(k); sel_dst.append((g * grp.S + slot) * P + j)
+    pts = pts_host.to(dev, non_blocking=True)
+    if sel_item:
+        xy = torch.empty(len(sel_item), 2, device=dev, dtype=torch.int32)
+        _l.check(L.as_norm_select(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), hp, wp, _p(rowcnt),
+                                  _p(_i32(sel_item, dev)), _p(_i32(sel_k, dev)), len(sel_item), _p(xy), _sp()), 'as_norm_select')
+        pts.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy
+    # ---- prototypes and refinement loop
+    GS = grp.G * grp.S
+    row_img = torch.arange(grp.G, dtype=torch.int32, device=dev).repeat_interleave(grp.S)
+    proto = torch.empty(grp.G, grp.S, C, device=dev, dtype=torch.float32)
+    _l.check(L.as_seed_proto(_p(feats), feats.stride(0), _p(row_img), _p(pts), GS, P, C, hp, wp, _p(proto), _sp()), 'as_seed_proto')
+    cur = cosine_maps(feats, grp.d_img, proto)
+    fg_low = torch.empty(n_tot, N, device=dev, dtype=torch.float32)
+    bg_low = torch.empty(n_tot, N, device=dev, dtype=torch.float32)
+    wsum = torch.empty(GS, device=dev, dtype=torch.float32)
+    nb = L.as_weighted_centroid_workspace(grp.G, grp.S, N, C)
+    ws = _ws(nb, dev)
+    centroid = proto
+    assert refine_times >= 1
+    for r in range(refine_times):
+        _l.check(L.as_refine_threshold(_p(cur), GS, N, float(obj_tau), _p(wsum), _sp()), 'as_refine_threshold')
+        centroid = torch.empty_like(proto)
+        _l.check(L.as_weighted_centroid(_p(feats), feats.stride(0), _p(grp.d_img), _p(cur), _p(wsum), grp.G, grp.S, N, C,
+                                        _p(centroid), _p(ws), nb, _sp()), 'as_weighted_centroid')
+        cur = cosine_maps(feats, grp.d_img, centroid)
+        _l.check(L.as_refine_select(_p(cur), grp.G, grp.S, N, wp, _p(grp.d_first), _p(grp.d_n), _p(rois),
+                                    int(r == refine_times - 1), _p(fg_low), _p(bg_low), _sp()), 'as_refine_select')
+    # ---- full resolution
+    map_fg = torch.empty(n_tot, H, W, device=dev, dtype=torch.float32)
+    map_bg = torch.empty(n_tot, H, W, device=dev, dtype=torch.float32) if want_bg else None
+    mask = torch.empty(n_tot, H, W, device=dev, dtype=torch.uint8) if want_mask else None
+    stats = torch.empty(n_tot * 3, device=dev, dtype=torch.int32)
+    _l.check(L.as_fuse_instance_maps(_p(fg_low), _p(bg_low), n_tot, hp, wp, float(mask_thr), _p(map_fg), _p(map_bg), _p(mask),
+                                     _p(stats), _sp()), 'as_fuse_instance_maps')
+    return dict(map_fg=map_fg, map_bg=map_bg, mask=mask, fg_low=fg_low, bg_low=bg_low, centroid=centroid, pts=pts, groups=grp)
+
+
+# --------------------------------------------------------------------------------------------------- A12
+def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, num_gt=20, corr_size=21):
+    """RH:1980-1990 + RH:433-461.  -> (coords [n_tot,num_gt,2] fp32 (x,y), labels [n_tot,num_gt] bool)."""
+    L = _l.load()
+    dev = map_fg.device
+    n_tot, H, W = map_fg.shape
+    pos = torch.empty(n_tot, H, W, device=dev, dtype=torch.uint8)
+    rowcnt = torch.empty(n_tot, H, 2, device=dev, dtype=torch.int32)
+    nbytes = L.as_mask_candidates_workspace(n_tot, H, W)
+    ws = _ws(nbytes, dev)
+    _l.check(L.as_mask_candidates(_p(map_fg), _p(map_bg), _p(rois), n_tot, H, W, float(pos_thr), float(neg_thr), int(corr_size),
+                                  _p(pos), _p(rowcnt), _p(ws), nbytes, _sp()), 'as_mask_candidates')
+    totals = rowcnt.sum(1).cpu().tolist()                    # host sync (2)
+    rois_i = rois.detach().cpu().int()
+    sel_obj, sel_kind, sel_k, sel_dst = [], [], [], []
+    coords = torch.zeros(n_tot, num_gt, 2, dtype=torch.float32)
+    labels = torch.zeros(n_tot, num_gt, dtype=torch.bool)
+    o = 0
+    for g, n in enumerate(n_per_img):
+        for j in range(n):
+            n_pos, n_neg = totals[o]
+            tot = n_pos + n_neg
+            chosen = rng.randperm_head((g, 1, j), tot, num_gt)
+            if chosen.shape[0] < num_gt:
+                if chosen.shape[0] == 0:                     # RH:452-455 sentinel (-1,-1), then the crop offset is added
+                    coords[o, :, 0] = -1.0 + float(rois_i[o, 0])
+                    coords[o, :, 1] = -1.0 + float(rois_i[o, 1])
+                    o += 1
+                    continue
+                chosen = _fill_index(chosen, num_gt)
+            for t, k in enumerate(chosen.tolist()):
+                is_pos = k < n_pos
+                sel_obj.append(o); sel_kind.append(0 if is_pos else 1); sel_k.append(k if is_pos else k - n_pos)
+                sel_dst.append(o * num_gt + t)
+                labels[o, t] = is_pos
+            o += 1
+    coords = coords.to(dev, non_blocking=True)
+    labels = labels.to(dev, non_blocking=True)
+    if sel_obj:
+        xy = torch.empty(len(sel_obj), 2, device=dev, dtype=torch.int32)
+        _l.check(L.as_mask_select(_p(pos), _p(map_bg), _p(rois), _p(ws), float(neg_thr), _p(rowcnt), _p(_i32(sel_obj, dev)),
+                                  _p(_i32(sel_kind, dev)), _p(_i32(sel_k, dev)), len(sel_obj), H, W, _p(xy), _sp()), 'as_mask_select')
+        coords.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy.float()
+    return coords, labels
+
+
+# --------------------------------------------------------------------------------------------------- A9 - A11
+def semantic_parts(map_fg, feats, obj_img, rois, hp, wp, pos_thr=0.6, n_shift=10, n_points=20, merge_thr=0.85,
+                   num_semantic_points=3, want_trace=False):
+    """RH:1995-2031 up to (not including) the ragged list assembly.  Everything stays on the device.
+    -> dict(fg_low, seed_map, seed_tok, prot, sim, keep, merged, n_merged, part_maps, centers, valid, part_id, cfeat, trace)."""
+    L = _l.load()
+    dev = map_fg.device
+    n_tot, H, W = map_fg.shape
+    N = hp * wp
+    C = feats.shape[2]
+    S = n_points
+    fg_low = torch.empty(n_tot, N, device=dev, dtype=torch.float32)
+    seed_map = torch.empty(n_tot, N, device=dev, dtype=torch.float32)
+    _l.check(L.as_erode_downsample(_p(map_fg), n_tot, H, W, float(pos_thr), 11, _p(fg_low), _p(seed_map), _sp()), 'as_erode_downsample')
+    seed_tok, proto0 = ops.grid_seeds(seed_map, feats, obj_img, rois, wp, S, thr=0.35)
+    prot, sim, trace = ops.mean_shift(proto0, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True,
+                                      want_trace=want_trace)
+    keep = torch.empty(n_tot, S, device=dev, dtype=torch.int32)
+    _l.check(L.as_filter_seeds(_p(sim), _p(fg_low), n_tot, S, N, 0.85, _p(keep), None, _sp()), 'as_filter_seeds')
+    merged = torch.empty(n_tot, S, C, device=dev, dtype=torch.float32)
+    n_merged = torch.empty(n_tot, device=dev, dtype=torch.int32)
+    _l.check(L.as_merge_prototypes(_p(prot), _p(keep), n_tot, S, C, float(merge_thr), _p(merged), _p(n_merged), _sp()), 'as_merge_prototypes')
+    pmaps = cosine_maps(feats, obj_img, merged)
+    KP = num_semantic_points + 1
+    centers = torch.empty(n_tot, KP, 2, device=dev, dtype=torch.float32)
+    valid = torch.empty(n_tot, KP, device=dev, dtype=torch.int32)
+    part_id = torch.empty(n_tot, KP, device=dev, dtype=torch.int32)
+    cfeat = torch.empty(n_tot, KP, C, device=dev, dtype=torch.float32)
+    stat = torch.empty(n_tot, S, 4, device=dev, dtype=torch.float32)
+    _l.check(L.as_part_centers(_p(pmaps), _p(n_merged), _p(rois), _p(feats), feats.stride(0), _p(obj_img), n_tot, S, N, C, wp, KP,
+                               _p(centers), _p(valid), _p(part_id), _p(cfeat), _p(stat), _sp()), 'as_part_centers')
+    return dict(fg_low=fg_low, seed_map=seed_map, seed_tok=seed_tok, prot=prot, sim=sim, keep=keep, merged=merged,
+                n_merged=n_merged, part_maps=pmaps, centers=centers, valid=valid, part_id=part_id, cfeat=cfeat, trace=trace)
+
+
+def assemble_parts(parts, n_per_img, gt_labels, hp, wp, num_max_keep=50):
+    """Build the reference's ragged python structures (RH:244-262, RH:2024-2031) per image.  One host sync (3)."""
+    n_merged = parts['n_merged'].cpu().tolist()
+    valid = parts['valid'].cpu().bool()
+    out = []
+    o = 0
+    dev = parts['centers'].device
+    for g, n in enumerate(n_per_img):
+        sl = slice(o, o + n)
+        v = valid[sl]
+        vd = v.to(dev)
+        coords = parts['centers'][sl][vd]
+        feats = parts['cfeat'][sl][vd]
+        split = v.sum(1).tolist()
+        owner = torch.arange(n).unsqueeze(1).expand_as(v)[v]
+        labels = gt_labels[g][owner.to(gt_labels[g].device)] if coords.shape[0] else gt_labels[g][:0]
+        sim_fg = [parts['part_maps'][o + j, :n_merged[o + j]].unflatten(-1, (hp, wp)) if n_merged[o + j] else torch.zeros(0, 0)
+                  for j in range(n)]
+        if coords.shape[0] == 0:
+            z2 = torch.zeros(0, 2, device=dev)
+            out.append(dict(semantic_centers=[z2, labels], semantic_centers_split=[], sim_fg=sim_fg,
+                            semantic_centers_feat_split=[], semantic_centers_feat=[], num_parts=split,
+                            semantic_centers_org=(z2.clone(), labels.clone()), corres_gts=torch.zeros(0, dtype=torch.long, device=dev)))
+        else:
+            c_org, l_org = coords.clone(), labels.clone()
+            if coords.shape[0] > num_max_keep:
+                pick = torch.randperm(coords.shape[0])[:num_max_keep].to(dev)
+                coords, labels = coords[pick], labels[pick]
+            out.append(dict(semantic_centers=[coords, labels], semantic_centers_split=list(c_org.split(split, dim=0)),
+                            sim_fg=sim_fg, semantic_centers_feat_split=list(feats.split(split, dim=0)),
+                            semantic_centers_feat=feats, num_parts=split, semantic_centers_org=(c_org, l_org),
+                            corres_gts=owner.to(dev)))
+        o += n
+    return out
+
+
+def cam_minmax(lows, hp, wp):
+    """min / max of the x16 bilinear up-sampling of every [hp,wp] map.  lows [n_maps, N] -> [n_maps, 2]."""
+    L = _l.load()
+    n_maps = lows.shape[0]
+    mm = torch.empty(n_maps, 2, device=lows.device, dtype=torch.float32)
+    scratch = torch.empty(n_maps * 2, device=lows.device, dtype=torch.int32)
+    _l.check(L.as_cam_minmax(_p(lows), n_maps, hp, wp, _p(mm), _p(scratch), _sp()), 'as_cam_minmax')
+    return mm

@@ -152,6 +152,7 @@ class VisionTransformerDet(nn.Module):
     def train(self, mode=True):     # VTD:153-156
         super().train(mode)
         self._freeze_stages()
+        return self
 
     def _freeze_stages(self):       # VTD:158-177
         if self.frozen_stages >= 0:

@@ -425,3 +425,23 @@ extern "C" int as_mean_shift(const float* feats, long long feat_img_stride, int 
   AS_LAUNCH_CHECK();
   return 0;
 }
+
+// Generic cosine maps: sim[g,s,n] = cos(protos[g,s,:], feats[grp_img[g], n, :])  (F.cosine_similarity semantics).
+// Used for the seed-prototype maps (RH:339), the refinement maps (RH:696) and the part maps (RH:297-301).
+extern "C" size_t as_cosine_maps_workspace(int n_img, int G, int S, int N, int C) {
+  return (((size_t)n_img * N * 4 + 255) & ~(size_t)255) + (size_t)G * S * C * 4;
+}
+extern "C" int as_cosine_maps(const float* feats, long long feat_img_stride, int n_img, int N, int C, const int* grp_img,
+                              const float* protos, int G, int S, float* sim, int clamp0, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream) {
+  if (G <= 0) return 0;
+  if (C % 4 || workspace_bytes < as_cosine_maps_workspace(n_img, G, S, N, C)) return AS_ERR_BAD_ARG;
+  float* den = (float*)workspace;
+  float* phat = (float*)((char*)workspace + (((size_t)n_img * N * 4 + 255) & ~(size_t)255));
+  ms_token_norm<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, den);
+  ms_proto_norm<<<G * S, 256, 0, stream>>>(protos, phat, C);
+  ms_sim<<<dim3((N + SIM_TOK - 1) / SIM_TOK, (S + SIM_SG - 1) / SIM_SG, G), SIM_TOK, 0, stream>>>(
+      feats, feat_img_stride, den, grp_img, nullptr, phat, N, C, N, 1, S, 0, clamp0, sim, nullptr, nullptr, nullptr);
+  AS_LAUNCH_CHECK();
+  return 0;
+}

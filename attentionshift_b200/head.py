@@ -1,0 +1,130 @@
+"""``AttnShiftRoIHead`` -- drop-in for the attention-shift part of the reference RoI head
+(mmdet/models/roi_heads/stdroi_point_deform_attn_reppoints.py, class at RH:1325, ``seed_pseudo_gt`` RH:2209-2415).
+
+Registered under BOTH names the reference configs use (``AttnShiftRoIHead`` in configs/mae/attnshift_voc12aug.py:60 and
+``StandardRoIHeadMaskPointSampleDeformAttnReppoints``, the class's actual name -- the reference's rename is incomplete).
+``seed_pseudo_gt`` keeps the reference signature and return keys; its body runs on the sm_100a kernels through
+``attention_shift``.  The two learned / host-side selections that sit in the middle of the reference function are
+outside this path and enter through hooks:
+  * point-token <-> GT matching (HungarianPointAssigner, scipy on the host in the reference): ``pos_inds`` kwarg, or the
+    built-in L1 Hungarian stand-in on the host;
+  * the MIL layer choice (RoIAlign + MAEBoxHeadMIL, RH:2953-2972): ``gt_index`` kwarg or ``mil_fn`` callable.
+The loss-side methods of the reference class (forward_train / simple_test) are not part of the hot path.
+"""
+import torch
+import torch.nn as nn
+
+from . import attention_shift as AS
+from .registry import HEADS
+
+
+@HEADS.register_module(name=['AttnShiftRoIHead', 'StandardRoIHeadMaskPointSampleDeformAttnReppoints'])
+class AttnShiftRoIHead(nn.Module):
+    def __init__(self, mil_head=None, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None, mask_head=None,
+                 shared_head=None, mae_head=None, bbox_rec_head=None, train_cfg=None, test_cfg=None, visualize=False,
+                 epoch=0, epoch_semantic_centers=0, num_semantic_points=3, semantic_to_token=False, pca_dim=128,
+                 mean_shift_times_local=10, reppoints_head=None, num_reppoints_head=1, n_seeds=20, mil_fn=None, rng=None):
+        super().__init__()
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        cfg = bbox_head if isinstance(bbox_head, dict) else {}
+        # CFG:102-105 -- the reference reads these off ``self.bbox_head``
+        self.cam_layer = int(cfg.get('cam_layer', 7))
+        self.seed_thr = float(cfg.get('seed_thr', 0.2))
+        self.seed_multiple = float(cfg.get('seed_multiple', 0.5))
+        self.visualize = visualize
+        self.epoch = epoch
+        self.epoch_semantic_centers = epoch_semantic_centers
+        self.num_semantic_points = num_semantic_points
+        self.semantic_to_token = semantic_to_token
+        self.pca_dim = pca_dim
+        self.mean_shift_times_local = mean_shift_times_local
+        self.n_seeds = n_seeds                  # 20 in the reference (hard-coded at RH:2024)
+        self.mil_fn = mil_fn
+        self.rng = rng if rng is not None else AS.KeyedRng(0)
+        self.with_mil = mil_head is not None or mil_fn is not None
+        self.with_deform_sup = False
+
+    # ---- stand-ins for the two out-of-path selections -------------------------------------------------
+    @staticmethod
+    def match_points(point_reg, gt_points, imgs_wh):
+        """Host Hungarian on the L1 distance between predicted (normalised) points and GT points -- the geometric term of
+        HungarianPointAssigner (hungarian_point_assigner.py:53-109).  -> list of LongTensor pos_inds (gt order)."""
+        from scipy.optimize import linear_sum_assignment
+        out = []
+        for i in range(point_reg.shape[0]):
+            pred = point_reg[i].detach().float().cpu()
+            gt = (gt_points[i].detach().float().cpu() / imgs_wh[i].detach().float().cpu().reshape(1, 2))
+            cost = torch.cdist(pred, gt, p=1)
+            r, c = linear_sum_assignment(cost.numpy())
+            order = torch.as_tensor(c).argsort()
+            out.append(torch.as_tensor(r)[order].long())
+        return out
+
+    def seed_pseudo_gt(self, x, img_metas, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore=None, gt_masks=None,
+                       vit_feat=None, img=None, point_init=None, point_cls=None, point_reg=None, imgs_whwh=None,
+                       attns=None, gt_points=None, gt_points_labels=None, roi_feature_map=None, return_mask=False,
+                       pos_mask_thr=0.6, neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, point_adjuster=None,
+                       edges=None, obj_tau=0.85, pos_inds=None, gt_index=None):
+        feats = AS.token_major(vit_feat)
+        if vit_feat.dim() == 4:
+            hp, wp = vit_feat.shape[-2:]
+        else:
+            hp, wp = x[2].shape[-2:]
+        dev = feats.device
+        B = feats.shape[0]
+        n_prop = point_cls.size(1) if point_cls is not None else attns[-1].shape[1] - 1 - hp * wp
+        if pos_inds is None:
+            wh = imgs_whwh.reshape(B, -1)[:, :2] if imgs_whwh is not None else torch.tensor([[wp * 16., hp * 16.]]).repeat(B, 1)
+            pos_inds = self.match_points(point_reg, gt_points, wh)
+        n_per_img = [int(p.shape[0]) for p in pos_inds]
+        obj_img = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(n_per_img)]).to(dev)
+        obj_pt = torch.cat([p.to(torch.int32) for p in pos_inds]).to(dev)
+        pts = torch.cat([p.float() for p in gt_points]).to(dev).contiguous()
+        labels = [gt_points_labels[i].to(dev) for i in range(B)]       # RH:2269 labels[i][pos_inds]: one label per matched GT
+        # A5-A7
+        rows = AS.rollout_rows(list(attns[-self.cam_layer:]), n_prop)
+        cams, mm, boxes, _ = AS.cam_boxes(rows, obj_img, obj_pt, pts, hp, wp, self.seed_thr, self.seed_multiple)
+        n_tot = obj_img.shape[0]
+        if gt_index is None:
+            if self.mil_fn is None:
+                raise ValueError('seed_pseudo_gt needs gt_index= or a mil_fn (MIL head is outside the hot path)')
+            gt_index = self.mil_fn(boxes.permute(1, 0, 2))
+        gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index
+        gt_index = gt_index.to(dev).long()
+        ar = torch.arange(n_tot, device=dev)
+        pseudo_boxes = boxes[gt_index, ar].contiguous()                # RH:2965-2967 gather of the chosen layer's box
+        cam_sel = cams[gt_index, ar].contiguous()
+        mm_sel = mm[gt_index, ar].contiguous()
+        # A8, A12, A13
+        rm = AS.refined_maps(cam_sel, mm_sel, feats, n_per_img, pseudo_boxes, pts, hp, wp, self.rng, refine_times=2,
+                             obj_tau=obj_tau, mask_thr=pos_mask_thr)
+        coords, plabels = AS.mask_points(rm['map_fg'], rm['map_bg'], pseudo_boxes, n_per_img, self.rng, pos_thr=pos_mask_thr,
+                                         neg_thr=neg_mask_thr, num_gt=num_mask_point_gt, corr_size=corr_size)
+        # A9-A11
+        parts = AS.semantic_parts(rm['map_fg'], feats, obj_img, pseudo_boxes, hp, wp, pos_thr=pos_mask_thr,
+                                  n_shift=self.mean_shift_times_local, n_points=self.n_seeds,
+                                  num_semantic_points=self.num_semantic_points)
+        per_img = AS.assemble_parts(parts, n_per_img, labels, hp, wp)
+        split = lambda t: list(t.split(n_per_img, dim=0))
+        masks = [m.cpu().numpy() for m in split(rm['mask'])] if return_mask else split(rm['mask'])   # RH:2358 D2H hand-off
+        grp = rm['groups']
+        fg_feat = [rm['centroid'][g, :n + 1].reshape(n + 1, -1, 1, 1) for g, n in enumerate(n_per_img)]
+        bg_feat = [rm['centroid'][g, n + 1:2 * n + 1].reshape(n, -1, 1, 1) for g, n in enumerate(n_per_img)]
+        out = dict(pseudo_gt_labels=labels, pseudo_gt_bboxes=split(pseudo_boxes), mil_losses={},
+                   best_attn_idx=split(gt_index), map_cos_fg=split(rm['map_fg']),
+                   mask_points_coords=split(coords), mask_points_labels=split(plabels),
+                   semantic_centers=[p['semantic_centers'] for p in per_img],
+                   semantic_centers_split=[p['semantic_centers_split'] for p in per_img],
+                   semantic_centers_feat_split=[p['semantic_centers_feat_split'] for p in per_img],
+                   semantic_centers_feat=[p['semantic_centers_feat'] for p in per_img],
+                   num_parts=[p['num_parts'] for p in per_img],
+                   semantic_centers_org=([p['semantic_centers_org'][0] for p in per_img],
+                                         [p['semantic_centers_org'][1] for p in per_img]),
+                   pseudo_gt_masks=masks, corres_gts=[p['corres_gts'] for p in per_img],
+                   inst_fg_feat=fg_feat, inst_bg_feat=bg_feat)
+        if self.visualize:
+            out.update(map_cos_bg=split(rm['map_bg']), sim_fg=[p['sim_fg'] for p in per_img], attns=cams,
+                       points_bg=rm['pts'], points_fg=rm['pts'])
+        self._last = dict(rows=rows, cams=cams, boxes=boxes, refined=rm, parts=parts)
+        return out

@@ -27,9 +27,71 @@ SIGNATURES = {
     'as_mean_shift_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_grid_seeds': (_i, [_vp, _f, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'as_mean_shift': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
+    'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'as_rollout_workspace': (_sz, [_i, _i, _i]),
+    'as_rollout_rows': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'as_cam_gather': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'as_cam_minmax': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    'as_cam_bbox_workspace': (_sz, [_i, _i, _i]),
+    'as_cam_bbox': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    'as_norm_rowcount': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'as_norm_select': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'as_seed_proto': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'as_refine_threshold': (_i, [_vp, _i, _i, _f, _vp, _vp]),
+    'as_weighted_centroid_workspace': (_sz, [_i, _i, _i, _i]),
+    'as_weighted_centroid': (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'as_refine_select': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    'as_fuse_instance_maps': (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    'as_mask_candidates_workspace': (_sz, [_i, _i, _i]),
+    'as_mask_candidates': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    'as_mask_select': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'as_erode_downsample': (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    'as_filter_seeds': (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    'as_merge_prototypes': (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    'as_part_centers': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
+
+
+class _Timers:
+    """Optional per-entry-point CUDA-event timing (bench.py): events are recorded on the launching stream around each
+    C-ABI call, so a family's time is the device time of the kernels that call enqueued."""
+
+    def __init__(self):
+        self.on = False
+        self.events = {}
+
+    def enable(self):
+        self.on = True
+        self.events = {}
+
+    def disable(self):
+        self.on = False
+
+    def wrap(self, name, fn):
+        def call(*a):
+            if not self.on:
+                return fn(*a)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a)
+            e.record()
+            self.events.setdefault(name, []).append((s, e))
+            return r
+        return call
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: dict(ms=sum(s.elapsed_time(e) for s, e in v), n=len(v)) for k, v in self.events.items()}
+
+
+TIMERS = _Timers()
+
+
+class _Lib:
+    pass
 
 
 class AttnShiftError(RuntimeError):
@@ -43,11 +105,14 @@ def load():
             raise AttnShiftError(
                 f'{LIB_PATH} not found -- build it with `python -m attentionshift_b200.build` '
                 '(there is no CPU / PyTorch fallback for the hot path)')
-        lib = ctypes.CDLL(LIB_PATH)
+        cdll = ctypes.CDLL(LIB_PATH)
+        lib = _Lib()
+        lib._cdll = cdll
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
+            fn = getattr(cdll, name)            # AttributeError here = header / library drift
             fn.restype = res
             fn.argtypes = args
+            setattr(lib, name, fn if name.endswith('_workspace') else TIMERS.wrap(name, fn))
         _lib = lib
     return _lib
 

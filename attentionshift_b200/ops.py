@@ -8,6 +8,7 @@ import torch
 from . import lib as _l
 
 EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 4
+TIMERS = _l.TIMERS
 
 
 def linear_f16(x, w, bias=None, mode=EPI_F16, resid=None):

@@ -78,9 +78,20 @@ except Exception:
     USING_MMDET = False
 
 
+def _register_all():
+    """importing the modules performs the registration (same side-effect mechanism as mmdet's __init__ files)."""
+    from . import backbone  # noqa: F401
+    try:
+        from . import head  # noqa: F401
+    except ImportError:
+        pass
+
+
 def build_backbone(cfg):
+    _register_all()
     return build_from_cfg(cfg, BACKBONES) if not USING_MMDET else BACKBONES.build(cfg)
 
 
 def build_head(cfg):
+    _register_all()
     return build_from_cfg(cfg, HEADS) if not USING_MMDET else HEADS.build(cfg)

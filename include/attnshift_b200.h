@@ -1,0 +1,146 @@
+/* attnshift_b200.h -- C ABI of libattnshift_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the AttentionShift hot path.  The reference has no native interface for this path (it is
+ * Python / PyTorch over mmdetection); each entry point below names the reference code it replaces:
+ *   VT  = models/vision_transformer.py
+ *   VTD = mmdet/models/backbones/visual_transformer_det.py
+ *   RH  = mmdet/models/roi_heads/stdroi_point_deform_attn_reppoints.py
+ * Python host code (attentionshift_b200/*.py) binds these with ctypes and keeps the mmdet registry surface
+ * (@BACKBONES VisionTransformerDet, @HEADS AttnShiftRoIHead); see INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless marked "host"; memory is allocated, owned and freed by the caller
+ *     (PyTorch); the library never allocates persistent device memory and never retains a pointer across calls;
+ *   - tensors are contiguous row-major unless a stride argument is given; "f16" = IEEE half stored in 2 bytes;
+ *   - every function enqueues on `stream` and returns without synchronising;
+ *   - return value 0 = success, a cudaError_t value, or AS_ERR_* (>10000); the only in-tree native precedent
+ *     (mmdet/ops/chamfer_2d/src/chamfer_2d.cu:135-141) likewise returns an int status;
+ *   - *_workspace() functions return the scratch size in bytes the matching call needs.
+ */
+#ifndef ATTNSHIFT_B200_H_
+#define ATTNSHIFT_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* as_stream_t; /* == cudaStream_t */
+
+#define AS_ERR_BAD_ARG 10001
+#define AS_ERR_NO_DRIVER 10002
+#define AS_ERR_TMAP 10003
+
+/* ------------------------------------------------------------------ ViT block (VT:62-124, VTD:192-275) */
+
+/* nn.Linear on tcgen05 tensor cores: y[M,N] = x[M,K] * w[N,K]^T + bias (VT:76/84 qkv / proj, VT:40-59 Mlp, VT:136 patch conv
+ * as GEMM).  mode 0: f16 out; 1: GELU(erf) -> f16 out (VT:55-56); 2: f32 out = resid + y (VT:114-115 residual); 4: f32 out. */
+int as_linear_f16(const void* x_f16, const void* w_f16, const float* bias, void* out, const float* resid, int M, int N,
+                  int K, int mode, as_stream_t stream);
+
+/* VT:76: qkv Linear fused with the reshape/permute to heads: q,k [B,h,T,64] f16, vt [B,h,64,Tpad] f16 (V transposed). */
+int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float* bias, void* q, void* k, void* vt, int B, int T,
+                    int Tpad, int heads, as_stream_t stream);
+
+/* VT:79-83: softmax(q k^T * 64^-0.5) v without materialising attn.  o [B,T,h*64] f16; m,l [B,h,T] f32 row statistics. */
+int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T, int Tpad,
+                int heads, as_stream_t stream);
+
+/* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,ceil(T/128)] per-tile row sums (may be NULL). */
+int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld, float* rowsum_part,
+                     int B, int T, int heads, as_stream_t stream);
+
+/* VT:110/114 LayerNorm (eps argument; 1e-6 at VT:146) with f16 output for the following GEMM. */
+int as_layernorm_f16(const float* x, const float* gamma, const float* beta, void* y_f16, int M, int C, float eps,
+                     as_stream_t stream);
+
+/* VT:136 / VTD:195 patch embedding operand: img [B,3,H,W] f32 -> [B*(H/16)*(W/16), 768] f16 rows (c, ky, kx). */
+int as_patch_im2col_f16(const float* img, void* cols_f16, int B, int H, int W, as_stream_t stream);
+
+/* VTD:203-213: x [B, 1+N+Tp, C] = [cls + pos0 | emb + pos | point tokens]. */
+int as_assemble_tokens(const float* emb, const float* cls, const float* pos, const float* ptok, float* x, int B, int N,
+                       int Tp, int C, as_stream_t stream);
+
+/* ------------------------------------------------------------------ attention roll-out (RH:1257-1272, RH:2272) */
+
+size_t as_rollout_workspace(int B, int T, int n_rows);
+/* attn / rowsum_part: HOST arrays of L device pointers (oldest layer first).  out [B,L,n_rows,T]. */
+int as_rollout_rows(const float* const* attn, const float* const* rowsum_part, int L, int B, int T, int ld, int ntile,
+                    int n_rows, float* out, void* workspace, size_t workspace_bytes, as_stream_t stream);
+
+/* ------------------------------------------------------------------ CAM -> pseudo box (RH:2272-2290, RH:60-116) */
+
+int as_cam_gather(const float* rows, const int* obj_img, const int* obj_pt, int L, int n_rows, int T, int N, int n_tot,
+                  float* cams, as_stream_t stream);
+int as_cam_minmax(const float* lows, int n_maps, int hp, int wp, float* minmax, void* scratch, as_stream_t stream);
+size_t as_cam_bbox_workspace(int n_maps, int H, int W);
+int as_cam_bbox(const float* lows, const float* minmax, const float* points, int n_maps, int n_tot, int hp, int wp,
+                float cam_thr, float area_ratio, float* boxes, unsigned char* keep_mask, void* workspace,
+                size_t workspace_bytes, as_stream_t stream);
+
+/* ------------------------------------------------------------------ cosine maps (RH:339, RH:696, RH:297-301) */
+
+size_t as_cosine_maps_workspace(int n_img, int G, int S, int N, int C);
+int as_cosine_maps(const float* feats, long long feat_img_stride, int n_img, int N, int C, const int* grp_img,
+                   const float* protos, int G, int S, float* sim, int clamp0, void* workspace, size_t workspace_bytes,
+                   as_stream_t stream);
+
+/* ------------------------------------------------------------------ refined instance maps (RH:1000-1046, RH:668-707) */
+
+int as_norm_rowcount(const float* low, const float* minmax, const int* item_kind, const int* item_a, const int* item_b,
+                     const float* item_thr, int n_items, int hp, int wp, int* rowcnt, as_stream_t stream);
+int as_norm_select(const float* low, const float* minmax, const int* item_kind, const int* item_a, const int* item_b,
+                   const float* item_thr, int hp, int wp, const int* rowcnt, const int* sel_item, const int* sel_k,
+                   int n_sel, int* out_xy, as_stream_t stream);
+int as_seed_proto(const float* feats, long long feat_img_stride, const int* row_img, const int* pts, int G, int P, int C,
+                  int hp, int wp, float* proto, as_stream_t stream);
+int as_refine_threshold(float* cur, int rows, int N, float tau, float* wsum, as_stream_t stream);
+size_t as_weighted_centroid_workspace(int G, int S, int N, int C);
+int as_weighted_centroid(const float* feats, long long feat_img_stride, const int* grp_img, const float* w,
+                         const float* wsum, int G, int S, int N, int C, float* out, void* workspace,
+                         size_t workspace_bytes, as_stream_t stream);
+int as_refine_select(float* cur, int G, int S, int N, int wp, const int* grp_first, const int* grp_nobj,
+                     const float* rois, int emit, float* fg_out, float* bg_out, as_stream_t stream);
+/* RH:1010-1019 + RH:2356: full-resolution fg / bg maps and uint8 pseudo masks from the low-resolution affinities. */
+int as_fuse_instance_maps(const float* fg_low, const float* bg_low, int n_tot, int hp, int wp, float mask_thr,
+                          float* map_fg, float* map_bg, unsigned char* mask, void* stats_scratch, as_stream_t stream);
+
+/* ------------------------------------------------------------------ mask-head point candidates (RH:433-461, RH:1980-1990) */
+
+size_t as_mask_candidates_workspace(int n_tot, int H, int W);
+int as_mask_candidates(const float* map_fg, const float* map_bg, const float* rois, int n_tot, int H, int W,
+                       float pos_thr, float neg_thr, int corr_size, unsigned char* pos, int* rowcnt, void* workspace,
+                       size_t workspace_bytes, as_stream_t stream);
+int as_mask_select(const unsigned char* pos, const float* map_bg, const float* rois, const void* workspace,
+                   float neg_thr, const int* rowcnt, const int* sel_obj, const int* sel_kind, const int* sel_k, int n_sel,
+                   int H, int W, int* out_xy, as_stream_t stream);
+
+/* ------------------------------------------------------------------ mean shift = the attention-shift loop
+ * (RH:1778-1840 seeds, RH:830-854 cosine_shift_batch, RH:882-908 update_density_batch, RH:2011-2020 seed map) */
+
+int as_erode_downsample(const float* map_fg, int n_tot, int H, int W, float thr, int corr_size, float* fg_low,
+                        float* seed_map, as_stream_t stream);
+int as_grid_seeds(const float* maps, float thr, const float* feats, long long feat_img_stride, const int* obj_img,
+                  const float* rois, int n_tot, int N, int C, int wp, int S, int* seed_tok, float* proto,
+                  as_stream_t stream);
+size_t as_mean_shift_workspace(int n_img, int n_tot, int S, int N, int C);
+int as_mean_shift(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
+                  const int* obj_img, const float* rois, int n_tot, int S, float* proto, float* sim, int n_shift,
+                  double tau0, double temp, int clamp0, int* trace, void* workspace, size_t workspace_bytes,
+                  as_stream_t stream);
+
+/* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
+
+int as_filter_seeds(const float* sim, const float* fg_low, int n_tot, int S, int N, float pos_thr, int* keep,
+                    float* score, as_stream_t stream);
+int as_merge_prototypes(const float* proto, const int* keep, int n_tot, int S, int C, float thr, float* merged,
+                        int* n_merged, as_stream_t stream);
+int as_part_centers(const float* pmap, const int* n_parts, const float* rois, const float* feats,
+                    long long feat_img_stride, const int* obj_img, int n_tot, int S, int N, int C, int wp, int KP,
+                    float* centers, int* valid, int* part_id, float* cfeat, float* stat_scratch, as_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATTNSHIFT_B200_H_ */

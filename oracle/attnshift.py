@@ -146,7 +146,7 @@ def norm_maps(maps):
     return (maps - mn) / (mx - mn)
 
 
-def sample_points(maps, num_points=10, thr=0.2, is_pos=False, gt_points=None):
+def sample_points(maps, num_points=10, thr=0.2, is_pos=False, gt_points=None, hook=None, keys=None):
     """RH:343-371 ``sample_point_grid``: per map, ``num_points`` random pixels (x, y)
     among those >= thr (is_pos) or < thr.  Consumes the torch CPU default generator
     exactly like the reference: one ``torch.randint(num, (len(arange(0,num,step)),))``
@@ -165,6 +165,8 @@ def sample_points(maps, num_points=10, thr=0.2, is_pos=False, gt_points=None):
                 cand = (m < thr * factor).nonzero(as_tuple=False)
                 num = cand.shape[0]
         step = num // num_points
+        if hook is not None:
+            hook(keys[i])                 # test harness only: re-seed per (image, stage, slot) -- see KeyedRng
         n_draw = torch.arange(0, num, step=step).shape
         idx = torch.randint(num, n_draw) % num
         out.append(cand[idx][:num_points])
@@ -228,16 +230,18 @@ def _normalize_map(m):
 
 
 def refined_maps(attn_maps, vit_feat, bboxes, thr_pos=0.2, thr_neg=0.1, num_points=20,
-                 refine_times=1, obj_tau=0.85, gt_points=None):
+                 refine_times=1, obj_tau=0.85, gt_points=None, hook=None, img=0):
     """RH:1000-1019 ``get_cosine_similarity_refined_map`` (+ RH:1042-1046).
 
     attn_maps [n_obj,H,W]; -> (fg [R+1,n_obj,H,W], bg [R+1,n_obj,H,W], points_fg
     [n_obj+1,P,2], points_bg [n_obj,P,2], fg_feat, bg_feat).  RNG draw order is
     bg, fg, bg_supp -- identical to the reference."""
     an = norm_maps(attn_maps)
-    pts_bg = sample_points(an, thr=thr_neg, num_points=num_points)
-    pts_fg = sample_points(an, thr=thr_pos, num_points=num_points, is_pos=True, gt_points=gt_points)
-    pts_supp = sample_points(an.mean(0, keepdim=True), thr=thr_neg, num_points=num_points)
+    n = an.shape[0]
+    pts_bg = sample_points(an, thr=thr_neg, num_points=num_points, hook=hook, keys=[(img, 0, n + 1 + j) for j in range(n)])
+    pts_fg = sample_points(an, thr=thr_pos, num_points=num_points, is_pos=True, gt_points=gt_points, hook=hook,
+                           keys=[(img, 0, j) for j in range(n)])
+    pts_supp = sample_points(an.mean(0, keepdim=True), thr=thr_neg, num_points=num_points, hook=hook, keys=[(img, 0, n)])
     pts_fg = torch.cat((pts_fg, pts_supp), dim=0)
     sim_fg, fg_feat = refined_similarity(pts_fg, vit_feat, bboxes, refine_times, obj_tau, is_select=True)
     sim_bg, bg_feat = refined_similarity(pts_bg, vit_feat, bboxes, refine_times, obj_tau)
@@ -271,13 +275,15 @@ def fill_index(idx, n):
     return fill_index(idx, n)
 
 
-def mask_points_in_box(map_fg, map_bg, pos_thr, neg_thr, num_gt, corr_size):
+def mask_points_in_box(map_fg, map_bg, pos_thr, neg_thr, num_gt, corr_size, hook=None, key=None):
     """RH:433-461 ``get_mask_points_single_box_cos_map_fg_bg`` on a box crop:
     candidates = eroded(fg > max*pos_thr) pixels (label 1) followed by
     (bg > max*neg_thr) pixels (label 0); pick ``torch.randperm(n)[:num_gt]``."""
     pos = erode((map_fg > map_fg.max() * pos_thr).float(), corr_size).nonzero(as_tuple=False)
     neg = (map_bg > map_bg.max() * neg_thr).nonzero(as_tuple=False)
     both = torch.cat((pos, neg), dim=0)
+    if hook is not None:
+        hook(key)
     chosen = torch.randperm(both.shape[0])[:num_gt]
     lab = torch.cat((torch.ones(pos.shape[0], dtype=torch.bool), torch.zeros(neg.shape[0], dtype=torch.bool)))
     if chosen.shape[0] < num_gt:
@@ -288,7 +294,7 @@ def mask_points_in_box(map_fg, map_bg, pos_thr, neg_thr, num_gt, corr_size):
 
 
 def mask_sample_points(attn, rois, attn_idx, vit_feat, pos_thr=0.6, neg_thr=0.6, num_gt=20,
-                       corr_size=21, refine_times=2, obj_tau=0.85, gt_points=None):
+                       corr_size=21, refine_times=2, obj_tau=0.85, gt_points=None, hook=None, img=0):
     """RH:1966-1993.  attn [L,n_obj,H,W] upsampled CAMs; attn_idx [n_obj] chosen layer
     per instance.  -> (coords [n_obj,num_gt,2] (x,y), labels [n_obj,num_gt] bool,
     map_fg, map_bg, points_bg(sic: fg), points_fg(sic: bg), feats_fg, feats_bg)
@@ -297,12 +303,12 @@ def mask_sample_points(attn, rois, attn_idx, vit_feat, pos_thr=0.6, neg_thr=0.6,
     amap = attn.detach().clone()[attn_idx, torch.arange(n)]
     fg, bg, p_fg, p_bg, f_fg, f_bg = refined_maps(amap, vit_feat, rois, thr_pos=0.2, thr_neg=0.1,
                                                   num_points=20, refine_times=refine_times,
-                                                  obj_tau=obj_tau, gt_points=gt_points)
+                                                  obj_tau=obj_tau, gt_points=gt_points, hook=hook, img=img)
     coords, labels = [], []
     for i in range(fg[0].shape[0]):
         x0, y0, x1, y1 = rois[i].int().tolist()
         c, l = mask_points_in_box(fg[-1][i][y0:y1, x0:x1], bg[-1][i][y0:y1, x0:x1],
-                                  pos_thr, neg_thr, num_gt, corr_size)
+                                  pos_thr, neg_thr, num_gt, corr_size, hook=hook, key=(img, 1, i))
         c[:, 0] += y0
         c[:, 1] += x0
         coords.append(c.flip(1))
@@ -492,16 +498,17 @@ def pseudo_masks(map_fg_last, pos_mask_thr):
 # --------------------------------------------------------------------------- A14 (per image chain)
 def attention_shift_image(cams_up, gt_index, pseudo_boxes, vit_feat, gt_points, gt_labels,
                           pos_mask_thr=0.6, neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21,
-                          obj_tau=0.85, mean_shift_times=10, num_semantic_points=3, n_points=20):
+                          obj_tau=0.85, mean_shift_times=10, num_semantic_points=3, n_points=20, hook=None, img=0,
+                          trace=None):
     """The per-image body of ``seed_pseudo_gt`` after the MIL selection (RH:2332-2361):
     refined fg/bg maps -> mask-head point labels -> semantic (part) centres -> pseudo
     instance masks.  Returns a dict with the keys of RH:2398-2415 that this path owns."""
     coords, labels, fg, bg, p_a, p_b, f_fg, f_bg = mask_sample_points(
         cams_up, pseudo_boxes, gt_index, vit_feat, pos_thr=pos_mask_thr, neg_thr=neg_mask_thr,
-        num_gt=num_mask_point_gt, corr_size=corr_size, obj_tau=obj_tau, gt_points=gt_points)
+        num_gt=num_mask_point_gt, corr_size=corr_size, obj_tau=obj_tau, gt_points=gt_points, hook=hook, img=img)
     sc = semantic_centers(fg[-1].clone(), bg[-1].clone(), pseudo_boxes, vit_feat, pos_thr=pos_mask_thr,
                           refine_times=mean_shift_times, gt_labels=gt_labels,
-                          num_semantic_points=num_semantic_points, n_points=n_points)
+                          num_semantic_points=num_semantic_points, n_points=n_points, trace=trace)
     return dict(mask_points_coords=coords, mask_points_labels=labels, map_cos_fg=fg[-1], map_cos_bg=bg[-1],
                 semantic_centers=sc[0], semantic_centers_split=sc[1], sim_fg=sc[2],
                 semantic_centers_feat_split=sc[3], semantic_centers_feat=sc[4], num_parts=sc[5],
