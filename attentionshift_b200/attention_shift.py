@@ -250,8 +250,9 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
     pts = pts_host.to(dev, non_blocking=True)
     if sel_item:
         xy = torch.empty(len(sel_item), 2, device=dev, dtype=torch.int32)
+        d_item, d_k = _i32(sel_item, dev), _i32(sel_k, dev)      # keep alive until enqueued (allocator reuse!)
         _l.check(L.as_norm_select(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), hp, wp, _p(rowcnt),
-                                  _p(_i32(sel_item, dev)), _p(_i32(sel_k, dev)), len(sel_item), _p(xy), _sp()), 'as_norm_select')
+                                  _p(d_item), _p(d_k), len(sel_item), _p(xy), _sp()), 'as_norm_select')
         pts.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy
     # ---- prototypes and refinement loop
     GS = grp.G * grp.S
@@ -324,8 +325,9 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
     labels = labels.to(dev, non_blocking=True)
     if sel_obj:
         xy = torch.empty(len(sel_obj), 2, device=dev, dtype=torch.int32)
-        _l.check(L.as_mask_select(_p(pos), _p(map_bg), _p(rois), _p(ws), float(neg_thr), _p(rowcnt), _p(_i32(sel_obj, dev)),
-                                  _p(_i32(sel_kind, dev)), _p(_i32(sel_k, dev)), len(sel_obj), H, W, _p(xy), _sp()), 'as_mask_select')
+        d_obj, d_kind, d_k = _i32(sel_obj, dev), _i32(sel_kind, dev), _i32(sel_k, dev)
+        _l.check(L.as_mask_select(_p(pos), _p(map_bg), _p(rois), _p(ws), float(neg_thr), _p(rowcnt), _p(d_obj),
+                                  _p(d_kind), _p(d_k), len(sel_obj), H, W, _p(xy), _sp()), 'as_mask_select')
         coords.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy.float()
     return coords, labels
 
