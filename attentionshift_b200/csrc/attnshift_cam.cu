@@ -87,81 +87,119 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-// label[p] = p if foreground else -1.  fg = (v - mn) / clamp(mx - mn, 1e-6) >= thr      (RH:63-66)
+// ---- run-based labelling.  A row's maximal foreground runs are the units: every pixel points at its run head, only
+// run heads carry areas / extents, and unions are issued only where a new adjacency can appear (8-connectivity):
+//   up fg            -> union(p, up)       unless left is fg (left already met `up` as its up-right neighbour)
+//   up bg, upleft fg -> union(p, upleft)   unless left is fg (left already met it as its `up`)
+//   up bg, upright fg-> union(p, upright)  always
+// label[p] = head index if foreground else -1;  runlen[head] = run length.
+// fg = (v - mn) / clamp(mx - mn, 1e-6) >= thr      (RH:63-66).   grid (H, n_maps), 256 threads, 4 pixels / thread
 __global__ void __launch_bounds__(256)
-ccl_init(const float* __restrict__ lows, const float* __restrict__ mmf, int hp, int wp, float thr, int* __restrict__ labels) {
-  extern __shared__ float low_s[];
-  const int m = blockIdx.y;
-  const int N = hp * wp, H = hp * 16, W = wp * 16;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) low_s[i] = lows[(size_t)m * N + i];
-  __syncthreads();
+ccl_init_runs(const float* __restrict__ lows, const float* __restrict__ mmf, int hp, int wp, float thr,
+              int* __restrict__ labels, int* __restrict__ runlen) {
+  __shared__ unsigned bits[128 + 1];              // foreground bitmap of the row (W <= 4096)
+  const int m = blockIdx.y, y = blockIdx.x;
+  const int H = hp * 16, W = wp * 16;
+  const int nw = (W + 31) / 32;
+  const float* low = lows + (size_t)m * hp * wp;
   const float mn = mmf[2 * m], den = fmaxf(mmf[2 * m + 1] - mn, 1e-6f);
-  int* lab = labels + (size_t)m * H * W;
-  const int total = H * W;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    const float v = (up16(low_s, hp, wp, p / W, p % W) - mn) / den;
-    lab[p] = (v >= thr) ? p : -1;
+  int* lab = labels + (size_t)m * H * W + (size_t)y * W;
+  int* rl = runlen + (size_t)m * H * W + (size_t)y * W;
+  const int lane = lane_id();
+  for (int x0 = (threadIdx.x >> 5) * 32; x0 < nw * 32; x0 += blockDim.x) {
+    const int x = x0 + lane;
+    const bool fg = x < W && ((up16(low, hp, wp, y, x) - mn) / den >= thr);
+    const unsigned b = __ballot_sync(0xffffffffu, fg);
+    if (lane == 0) bits[x0 >> 5] = b;
+  }
+  if (threadIdx.x == 0) bits[nw] = 0u;             // sentinel: background past the row end
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    int w = x >> 5;
+    const int bpos = x & 31;
+    if (!((bits[w] >> bpos) & 1u)) { lab[x] = -1; continue; }
+    // nearest background bit to the left -> run start
+    unsigned inv = ~bits[w] & ((1u << bpos) - 1u);
+    int start;
+    if (inv) {
+      start = (w << 5) + 32 - __clz(inv);
+    } else {
+      int ww = w - 1;
+      while (ww >= 0 && bits[ww] == 0xffffffffu) --ww;
+      start = ww < 0 ? 0 : (ww << 5) + 32 - __clz(~bits[ww]);
+    }
+    lab[x] = (int)((size_t)y * W + start);
+    if (start == x) {                               // run head: nearest background bit to the right -> run end
+      inv = ~bits[w] & ~((bpos == 31) ? 0xffffffffu : ((2u << bpos) - 1u));
+      int end;
+      if (inv) {
+        end = (w << 5) + __ffs(inv) - 1;
+      } else {
+        int ww = w + 1;
+        while (bits[ww] == 0xffffffffu) ++ww;        // bits[nw] == 0 terminates
+        end = (ww << 5) + __ffs(~bits[ww]) - 1;
+      }
+      rl[x] = min(end, W) - x;
+    }
   }
 }
 
-__global__ void ccl_merge(int* __restrict__ labels, int H, int W) {
+__global__ void ccl_merge_runs(int* __restrict__ labels, int H, int W) {
   int* lab = labels + (size_t)blockIdx.y * H * W;
   const int total = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    if (lab[p] < 0) continue;
-    const int y = p / W, x = p - y * W;
-    if (x > 0 && lab[p - 1] >= 0) uf_union(lab, p, p - 1);
-    if (y > 0) {
-      if (lab[p - W] >= 0) uf_union(lab, p, p - W);
-      if (x > 0 && lab[p - W - 1] >= 0) uf_union(lab, p, p - W - 1);
+    if (p < W || lab[p] < 0) continue;
+    const int x = p % W;
+    const bool left = x > 0 && lab[p - 1] >= 0;
+    const bool up = lab[p - W] >= 0;
+    if (up) {
+      if (!left) uf_union(lab, p, p - W);
+    } else {
+      if (!left && x > 0 && lab[p - W - 1] >= 0) uf_union(lab, p, p - W - 1);
       if (x + 1 < W && lab[p - W + 1] >= 0) uf_union(lab, p, p - W + 1);
     }
   }
 }
 
-// flatten + component areas
-__global__ void ccl_flatten_area(int* __restrict__ labels, int* __restrict__ area, int H, int W) {
+// per run head: root, area accumulation (one atomic per run)
+__global__ void ccl_run_area(int* __restrict__ labels, const int* __restrict__ runlen, int* __restrict__ area, int H, int W) {
   int* lab = labels + (size_t)blockIdx.y * H * W;
+  const int* rl = runlen + (size_t)blockIdx.y * H * W;
   int* ar = area + (size_t)blockIdx.y * H * W;
   const int total = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    if (lab[p] < 0) continue;
+    const int len = rl[p];
+    if (len <= 0) continue;                 // not a run head
     const int r = uf_find(lab, p);
-    atomicAdd(&ar[r], 1);
+    atomicAdd(&ar[r], len);
   }
 }
-__global__ void ccl_max_area(const int* __restrict__ labels, const int* __restrict__ area, int H, int W,
-                             int* __restrict__ max_area) {
-  const int* lab = labels + (size_t)blockIdx.y * H * W;
+__global__ void ccl_max_area(const int* __restrict__ area, int H, int W, int* __restrict__ max_area) {
   const int* ar = area + (size_t)blockIdx.y * H * W;
   const int total = H * W;
   int best = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x)
-    if (ar[p] > best) best = ar[p];
-  (void)lab;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) best = max(best, ar[p]);
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
   if (lane_id() == 0 && best > 0) atomicMax(max_area + blockIdx.y, best);
 }
-// extent of the kept components; ext[m] = {xmin, ymin, xmax, ymax} (ints, init {INT_MAX, INT_MAX, -1, -1})
-__global__ void ccl_extent(const int* __restrict__ labels, const int* __restrict__ area, const int* __restrict__ max_area,
-                           float ratio, int H, int W, int* __restrict__ ext, unsigned char* __restrict__ keep_mask) {
+// extent of the kept components from the run heads; ext[m] = {xmin, ymin, xmax, ymax}
+__global__ void ccl_run_extent(int* __restrict__ labels, const int* __restrict__ runlen, const int* __restrict__ area,
+                               const int* __restrict__ max_area, float ratio, int H, int W, int* __restrict__ ext) {
   const int m = blockIdx.y;
-  int* lab = const_cast<int*>(labels) + (size_t)m * H * W;
+  int* lab = labels + (size_t)m * H * W;
+  const int* rl = runlen + (size_t)m * H * W;
   const int* ar = area + (size_t)m * H * W;
   const float need = ratio * (float)max_area[m];
   const int total = H * W;
   int x0 = INT_MAX, y0 = INT_MAX, x1 = -1, y1 = -1;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    bool keep = false;
-    if (lab[p] >= 0) {
-      const int r = uf_find(lab, p);
-      keep = (float)ar[r] >= need;
-      if (keep) {
-        const int y = p / W, x = p - y * W;
-        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
-      }
+    const int len = rl[p];
+    if (len <= 0) continue;
+    const int r = uf_find(lab, p);
+    if ((float)ar[r] >= need) {
+      const int y = p / W, x = p - y * W;
+      x0 = min(x0, x); x1 = max(x1, x + len - 1); y0 = min(y0, y); y1 = max(y1, y);
     }
-    if (keep_mask) keep_mask[(size_t)m * total + p] = keep;
   }
   for (int o = 16; o > 0; o >>= 1) {
     x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
@@ -170,6 +208,20 @@ __global__ void ccl_extent(const int* __restrict__ labels, const int* __restrict
   if (lane_id() == 0 && x1 >= 0) {
     atomicMin(ext + 4 * m, x0); atomicMin(ext + 4 * m + 1, y0);
     atomicMax(ext + 4 * m + 2, x1); atomicMax(ext + 4 * m + 3, y1);
+  }
+}
+// optional (tests / visualisation): the reference's remained_label_masks
+__global__ void ccl_keep_mask(int* __restrict__ labels, const int* __restrict__ area, const int* __restrict__ max_area,
+                              float ratio, int H, int W, unsigned char* __restrict__ keep_mask) {
+  const int m = blockIdx.y;
+  int* lab = labels + (size_t)m * H * W;
+  const int* ar = area + (size_t)m * H * W;
+  const float need = ratio * (float)max_area[m];
+  const int total = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    bool keep = false;
+    if (lab[p] >= 0) keep = (float)ar[uf_find(lab, p)] >= need;
+    keep_mask[(size_t)m * total + p] = keep;
   }
 }
 __global__ void ext_init(int* ext, int n) {
@@ -221,7 +273,7 @@ extern "C" int as_cam_minmax(const float* lows, int n_maps, int hp, int wp, floa
 }
 
 extern "C" size_t as_cam_bbox_workspace(int n_maps, int H, int W) {
-  return (size_t)n_maps * H * W * 8 + (size_t)n_maps * 5 * 4 + 1024;
+  return (size_t)n_maps * H * W * 12 + (size_t)n_maps * 5 * 4 + 1024;
 }
 
 // boxes [n_maps,4] for maps ordered [layer][instance] (n_maps = L * n_tot); points [n_tot,2].
@@ -231,21 +283,21 @@ extern "C" int as_cam_bbox(const float* lows, const float* minmax, const float* 
                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (n_maps <= 0) return 0;
   const int H = hp * 16, W = wp * 16;
-  if (workspace_bytes < as_cam_bbox_workspace(n_maps, H, W)) return AS_ERR_BAD_ARG;
+  if (W > 4096 || workspace_bytes < as_cam_bbox_workspace(n_maps, H, W)) return AS_ERR_BAD_ARG;
   int* labels = (int*)workspace;
   int* area = labels + (size_t)n_maps * H * W;
-  int* max_area = area + (size_t)n_maps * H * W;
+  int* runlen = area + (size_t)n_maps * H * W;
+  int* max_area = runlen + (size_t)n_maps * H * W;
   int* ext = max_area + n_maps;
-  const size_t smem = (size_t)hp * wp * 4;
-  AS_CUDA(cudaFuncSetAttribute(ccl_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  AS_CUDA(cudaMemsetAsync(area, 0, ((size_t)n_maps * H * W + n_maps) * 4, stream));
+  AS_CUDA(cudaMemsetAsync(area, 0, ((size_t)2 * n_maps * H * W + n_maps) * 4, stream));   // area, runlen, max_area
   ext_init<<<(4 * n_maps + 255) / 256, 256, 0, stream>>>(ext, 4 * n_maps);
-  const dim3 grid(64, n_maps);
-  ccl_init<<<grid, 256, smem, stream>>>(lows, minmax, hp, wp, cam_thr, labels);
-  ccl_merge<<<grid, 256, 0, stream>>>(labels, H, W);
-  ccl_flatten_area<<<grid, 256, 0, stream>>>(labels, area, H, W);
-  ccl_max_area<<<grid, 256, 0, stream>>>(labels, area, H, W, max_area);
-  ccl_extent<<<grid, 256, 0, stream>>>(labels, area, max_area, area_ratio, H, W, ext, keep_mask);
+  const dim3 grid(74, n_maps);
+  ccl_init_runs<<<dim3(H, n_maps), 256, 0, stream>>>(lows, minmax, hp, wp, cam_thr, labels, runlen);
+  ccl_merge_runs<<<grid, 256, 0, stream>>>(labels, H, W);
+  ccl_run_area<<<grid, 256, 0, stream>>>(labels, runlen, area, H, W);
+  ccl_max_area<<<grid, 256, 0, stream>>>(area, H, W, max_area);
+  ccl_run_extent<<<grid, 256, 0, stream>>>(labels, runlen, area, max_area, area_ratio, H, W, ext);
+  if (keep_mask) ccl_keep_mask<<<grid, 256, 0, stream>>>(labels, area, max_area, area_ratio, H, W, keep_mask);
   cam_expand_box<<<(n_maps + 127) / 128, 128, 0, stream>>>(ext, points, n_tot, n_maps, (float)W, (float)H, boxes);
   AS_LAUNCH_CHECK();
   return 0;
