@@ -113,9 +113,10 @@ def token_major(vit_feat):
 
 
 # --------------------------------------------------------------------------------------------------- A5: roll-out
-def rollout_rows(attns, n_rows):
+def rollout_rows(attns, n_rows, use_tensor_cores=True):
     """RH:1257-1272 restricted to the last ``n_rows`` rows.  attns: list of L tensors [B,T,T] (row stride may be padded).
-    -> [B, L, n_rows, T] (index 0 = last layer alone)."""
+    -> [B, L, n_rows, T] view (index 0 = last layer alone).  When the maps carry the split-fp16 transposed copies written
+    by the head-mean kernel (``_as_t16``) the products run on the tensor cores; otherwise on the fp32 CUDA-core slab GEMM."""
     L = _l.load()
     nl = len(attns)
     B, T, _ = attns[0].shape
@@ -127,9 +128,21 @@ def rollout_rows(attns, n_rows):
         p = getattr(a, '_as_rowsum_part', None)
         parts.append(p if p is not None else a.sum(-1, keepdim=True).contiguous())
     ntile = parts[0].shape[2]
-    out = torch.empty(B, nl, n_rows, T, device=dev, dtype=torch.float32)
     a_ptrs = (ctypes.c_void_p * nl)(*[a.data_ptr() for a in attns])
     p_ptrs = (ctypes.c_void_p * nl)(*[p.data_ptr() for p in parts])
+    t16 = [getattr(a, '_as_t16', None) for a in attns]
+    if use_tensor_cores and all(t is not None for t in t16[:-1]) and n_rows <= 128:
+        ldt = (T + 127) // 128 * 128
+        dummy = t16[0][0] if t16[0] is not None else attns[0]
+        h_ptrs = (ctypes.c_void_p * nl)(*[(t[0] if t is not None else dummy).data_ptr() for t in t16])
+        l_ptrs = (ctypes.c_void_p * nl)(*[(t[1] if t is not None else dummy).data_ptr() for t in t16])
+        out = torch.empty(B, nl, n_rows, ldt, device=dev, dtype=torch.float32)
+        nbytes = L.as_rollout_tc_workspace(B, T, ldt)
+        ws = _ws(nbytes, dev)
+        _l.check(L.as_rollout_rows_tc(a_ptrs, h_ptrs, l_ptrs, p_ptrs, nl, B, T, ld, ldt, ops.T_SCALE, ntile, n_rows, _p(out),
+                                      _p(ws), nbytes, _sp()), 'as_rollout_rows_tc')
+        return out[..., :T]
+    out = torch.empty(B, nl, n_rows, T, device=dev, dtype=torch.float32)
     nbytes = L.as_rollout_workspace(B, T, n_rows)
     ws = _ws(nbytes, dev)
     _l.check(L.as_rollout_rows(a_ptrs, p_ptrs, nl, B, T, ld, ntile, n_rows, _p(out), _p(ws), nbytes, _sp()), 'as_rollout_rows')
@@ -146,8 +159,10 @@ def cam_boxes(rows, obj_img, obj_pt, gt_points, hp, wp, cam_thr=0.2, area_ratio=
     n_tot = obj_img.shape[0]
     N = hp * wp
     dev = rows.device
+    ldr = rows.stride(2)
+    assert rows.stride(3) == 1 and rows.stride(1) == n_rows * ldr and rows.stride(0) == nl * n_rows * ldr
     cams = torch.empty(nl, n_tot, N, device=dev, dtype=torch.float32)
-    _l.check(L.as_cam_gather(_p(rows), _p(obj_img), _p(obj_pt), nl, n_rows, T, N, n_tot, _p(cams), _sp()), 'as_cam_gather')
+    _l.check(L.as_cam_gather(_p(rows), _p(obj_img), _p(obj_pt), nl, n_rows, ldr, N, n_tot, _p(cams), _sp()), 'as_cam_gather')
     n_maps = nl * n_tot
     mm = torch.empty(n_maps, 2, device=dev, dtype=torch.float32)
     scratch = torch.empty(n_maps * 2, device=dev, dtype=torch.int32)

@@ -25,7 +25,7 @@ __device__ __forceinline__ float dec_f(unsigned u) {
 
 // cams[l, o, n] = rows[img(o), l, point(o), 1 + n]      rows: [B, L, n_rows, T]
 __global__ void cam_gather(const float* __restrict__ rows, const int* __restrict__ obj_img, const int* __restrict__ obj_pt,
-                           int L, int n_rows, int T, int N, int n_tot, float* __restrict__ cams) {
+                           int L, int n_rows, int T /* row stride */, int N, int n_tot, float* __restrict__ cams) {
   const int o = blockIdx.y, l = blockIdx.z;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;

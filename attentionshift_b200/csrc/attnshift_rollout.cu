@@ -5,6 +5,7 @@
 //   R_0 = aug_last[-n_rows:],   R_i = R_{i-1} @ aug_{last-i}
 // with  R @ aug = R' @ A + R',  R'[r,k] = R[r,k] / rs[k],  rs[k] = rowsum(A)[k] + 1   (A = head-mean attention).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 using namespace asb;
 
@@ -94,7 +95,78 @@ rollout_gemm(const float* __restrict__ Rp, const float* __restrict__ A, int ld, 
   }
 }
 
+// tensor-core path helpers: the slab R' as split-fp16 A operand [B,128,ldk] (zero padded) and R' itself (the identity
+// term of aug) written straight into the output slab, where the three GEMMs then accumulate.
+__global__ void rollout_scale_split(const float* __restrict__ R, size_t r_bstride, int ldr, const float* __restrict__ rs, int T,
+                                    int n_rows, int ldk, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    float* __restrict__ out, size_t out_bstride, int ldo) {
+  const int b = blockIdx.z, r = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ldk) return;
+  float v = 0.f;
+  if (r < n_rows && k < T) v = R[b * r_bstride + (size_t)r * ldr + k] / rs[(size_t)b * T + k];
+  const float sv = v * scale;
+  const __half h = __float2half_rn(sv);
+  hi[((size_t)b * 128 + r) * ldk + k] = h;
+  lo[((size_t)b * 128 + r) * ldk + k] = __float2half_rn(sv - __half2float(h));
+  if (r < n_rows && k < ldo) out[b * out_bstride + (size_t)r * ldo + k] = v;
+}
+__global__ void rollout_first_ld(const float* __restrict__ A, int ld, const float* __restrict__ rs, int T, int n_rows,
+                                 float* __restrict__ out, size_t out_bstride, int ldo) {
+  const int b = blockIdx.z, r = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ldo) return;
+  const int row = T - n_rows + r;
+  float v = 0.f;
+  if (n < T) v = (A[((size_t)b * T + row) * ld + n] + (n == row ? 1.f : 0.f)) / rs[(size_t)b * T + row];
+  out[b * out_bstride + (size_t)r * ldo + n] = v;
+}
+
 }  // namespace
+
+extern "C" int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M,
+                                int N, int K, int x_rows, int w_rows, int ldo, long long out_bstride, float alpha,
+                                cudaStream_t stream);
+
+extern "C" size_t as_rollout_tc_workspace(int B, int T, int ldt) {
+  return ((size_t)B * T * 4 + 255) / 256 * 256 + (size_t)2 * B * 128 * ldt * 2;
+}
+
+// Tensor-core roll-out.  attn[l] [B,T,ld] f32 (only the LAST layer's map is read: its last n_rows rows), t_hi[l] / t_lo[l]
+// [B,ldt,ldt] split-fp16 transposed maps scaled by t_scale (as written by as_attn_headmean), rowsum_part as above.
+// out [B, L, n_rows, ldt] f32 (row stride ldt; columns >= T are zero).
+extern "C" int as_rollout_rows_tc(const float* const* attn, const void* const* t_hi, const void* const* t_lo,
+                                  const float* const* rowsum_part, int L, int B, int T, int ld, int ldt, float t_scale,
+                                  int ntile, int n_rows, float* out, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream) {
+  if (n_rows > 128 || n_rows > T || L < 1 || ldt % 64 || ldt < T) return AS_ERR_BAD_ARG;
+  if (workspace_bytes < as_rollout_tc_workspace(B, T, ldt)) return AS_ERR_BAD_ARG;
+  float* rs = (float*)workspace;
+  __half* hi = (__half*)((char*)workspace + ((size_t)B * T * 4 + 255) / 256 * 256);
+  __half* lo = hi + (size_t)B * 128 * ldt;
+  const size_t bstride = (size_t)L * n_rows * ldt;
+  const float r_scale = 4096.f;                                   // 2^12: keeps the lo halves out of the fp16 subnormals
+  const float alpha = 1.f / (r_scale * t_scale);
+  for (int i = 0; i < L; ++i) {
+    const int l = L - 1 - i;
+    rollout_rowsum<<<(B * T + 255) / 256, 256, 0, stream>>>(rowsum_part[l], ntile, B * T, rs);
+    float* dst = out + (size_t)i * n_rows * ldt;
+    if (i == 0) {
+      rollout_first_ld<<<dim3((ldt + 255) / 256, n_rows, B), 256, 0, stream>>>(attn[l], ld, rs, T, n_rows, dst, bstride, ldt);
+    } else {
+      rollout_scale_split<<<dim3((ldt + 255) / 256, 128, B), 256, 0, stream>>>(out + (size_t)(i - 1) * n_rows * ldt, bstride, ldt, rs, T,
+                                                                             n_rows, ldt, r_scale, hi, lo, dst, bstride, ldt);
+      int r = as_bgemm_f16_f32(hi, t_hi[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
+      if (r) return r;
+      r = as_bgemm_f16_f32(hi, t_lo[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
+      if (r) return r;
+      r = as_bgemm_f16_f32(lo, t_hi[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
+      if (r) return r;
+    }
+  }
+  AS_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t as_rollout_workspace(int B, int T, int n_rows) {
   return ((size_t)B * T * 4 + 255) / 256 * 256 + (size_t)B * n_rows * T * 4;

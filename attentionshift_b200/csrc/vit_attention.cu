@@ -10,7 +10,8 @@
 //                    Outputs O [B,T,C] fp16 and the per-row log2-domain max m and denominator l [B,h,T].
 // as_attn_headmean : second pass for layers whose attention map is consumed: for a (128 x 128) tile loops the heads,
 //                    recomputes S_h on tensor cores and accumulates exp2(S_h*c - m_h) / l_h in registers; writes the
-//                    head-mean tile once (+ deterministic row-sum partials for the roll-out normaliser).
+//                    head-mean tile once (+ deterministic row-sum partials for the roll-out normaliser, and optionally
+//                    the transposed map as a split-fp16 pair = the K-major B operand of the roll-out GEMM).
 #include "common.cuh"
 #include <math.h>
 
@@ -132,53 +133,71 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       const int kv0 = j * BKV;
       const bool tail = kv0 + BKV > p.T;
-      // pass 1: row maximum of the scaled logits
+      // pass 1: row maximum of the scaled logits (two 32-column chunks in flight per TMEM wait)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + COL_S + c * 32, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(lane_addr + COL_S + c * 32, va);
+        tmem_ld_32x32(lane_addr + COL_S + c * 32 + 32, vb);
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (tail && kv0 + c * 32 + i >= p.T) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          float s0 = __uint_as_float(va[i]), s1 = __uint_as_float(vb[i]);
+          if (tail) {
+            if (kv0 + c * 32 + i >= p.T) s0 = -INFINITY;
+            if (kv0 + c * 32 + 32 + i >= p.T) s1 = -INFINITY;
+          }
+          mx = fmaxf(mx, fmaxf(s0, s1));
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);       // 0 on the first tile (m_run = -inf)
+      // lazy rescaling: the running offset m_run only moves when some row of the warp would otherwise exceed 2^8
+      // (P is fp16: values up to 256 are exact enough and far from overflow); most tiles skip the O read-modify-write
+      const float tmax = mx * p.scale_log2;
+      const bool need = __any_sync(0xffffffffu, tmax > m_run + 8.f);
+      float alpha = 1.f;
+      if (need) {
+        const float m_new = fmaxf(m_run, tmax);
+        alpha = ex2_approx(m_run - m_new);                  // 0 on the first tile (m_run = -inf)
+        m_run = m_new;
+      }
       if (j > 0) mbar_wait(pv_done, (j - 1) & 1);            // P buffer and O accumulator are free again
       tc_fence_after();
       // pass 2: p = exp2(s*c - m), packed fp16 into the P columns
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + COL_S + c * 32, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(lane_addr + COL_S + c * 32, va);
+        tmem_ld_32x32(lane_addr + COL_S + c * 32 + 32, vb);
         tc_wait_ld();
-        uint32_t pk[16];
+        uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-          float p0 = ex2_approx(fmaf(s0, p.scale_log2, -m_new));
-          float p1 = ex2_approx(fmaf(s1, p.scale_log2, -m_new));
+          // (an FMA-pipe polynomial exp2 for half of the elements was measured SLOWER on B200: 3-register FFMAs issue
+          //  every other cycle per scheduler, so 9 extra FMA/ALU instructions cost more than the MUFU slot they free)
+          float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * i]), p.scale_log2, -m_run));
+          float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * i + 1]), p.scale_log2, -m_run));
+          float p2 = ex2_approx(fmaf(__uint_as_float(vb[2 * i]), p.scale_log2, -m_run));
+          float p3 = ex2_approx(fmaf(__uint_as_float(vb[2 * i + 1]), p.scale_log2, -m_run));
           if (tail) {
             if (kv0 + c * 32 + 2 * i >= p.T) p0 = 0.f;
             if (kv0 + c * 32 + 2 * i + 1 >= p.T) p1 = 0.f;
+            if (kv0 + c * 32 + 32 + 2 * i >= p.T) p2 = 0.f;
+            if (kv0 + c * 32 + 33 + 2 * i >= p.T) p3 = 0.f;
           }
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+          sum += (p0 + p1) + (p2 + p3);
+          __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h01);
+          pk[16 + i] = *reinterpret_cast<uint32_t*>(&h23);
         }
-        tmem_st_32x16(lane_addr + COL_P + c * 16, pk);
+        tmem_st_32x32(lane_addr + COL_P + c * 16, pk);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);                  // S fully read: the next Q K^T may overwrite it
       l_run = l_run * alpha + sum;
-      m_run = m_new;
-      if (j > 0) {                                          // rescale the running output
+      if (need && j > 0) {                                  // rescale the running output (warp-uniform branch)
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
@@ -229,10 +248,12 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ head-mean probabilities
-constexpr int HM_THREADS = 192;
-constexpr int HM_SMEM_TILES = 4 * TILE_BYTES;               // 2 stages x (Q_h, K_h)
+constexpr int HM_THREADS = 320;   // TMA warp, MMA warp, 2 x 4 math warps (each quartet covers 64 of the 128 key columns)
+constexpr int HM_STAGES = 4;
+constexpr int HM_SMEM_TILES = 2 * HM_STAGES * TILE_BYTES;     // HM_STAGES x (Q_h, K_h)
 constexpr int HM_STAGE_LD = 129;                            // floats per staged output row (padded: conflict-free)
-constexpr int HM_SMEM = HM_SMEM_TILES + 1024 + 256 + BQ * HM_STAGE_LD * 4;
+constexpr int HM_MAX_HEADS = 16;
+constexpr int HM_SMEM = HM_SMEM_TILES + 1024 + 256 + BQ * HM_STAGE_LD * 4 + HM_MAX_HEADS * BQ * 8;
 
 struct HmParams {
   int T, heads, ld;           // ld = row stride (floats) of the output
@@ -242,6 +263,10 @@ struct HmParams {
   float* out;                 // [B, T, ld]
   float* rowsum_part;         // [B, T, ntile] or null
   int ntile;
+  __half* t_hi;               // optional: TRANSPOSED map, split fp16 (hi + lo), scaled: [B, ldt, ldt], fully written
+  __half* t_lo;
+  int ldt;
+  float t_scale;
 };
 
 __global__ void __launch_bounds__(HM_THREADS, 1)
@@ -249,19 +274,18 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HM_SMEM_TILES);
-  uint64_t* full = bars;        // 2
-  uint64_t* empty = bars + 2;   // 2
-  uint64_t* s_full = bars + 4;  // 2
-  uint64_t* s_empty = bars + 6; // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* full = bars;                       // HM_STAGES
+  uint64_t* empty = bars + HM_STAGES;          // HM_STAGES
+  uint64_t* s_full = bars + 2 * HM_STAGES;     // 2 (TMEM S buffers)
+  uint64_t* s_empty = bars + 2 * HM_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HM_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-    }
+    for (int i = 0; i < HM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -273,8 +297,8 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     if (elect_one()) {
       for (int h = 0; h < p.heads; ++h) {
-        const int st = h & 1;
-        mbar_wait(&empty[st], ((h >> 1) & 1) ^ 1);
+        const int st = h % HM_STAGES;
+        mbar_wait(&empty[st], ((h / HM_STAGES) & 1) ^ 1);
         mbar_expect_tx(&full[st], 2 * TILE_BYTES);
         tma_load_3d(smem + (2 * st) * TILE_BYTES, &tm_q, &full[st], 0, qt * BQ, b * p.heads + h);
         tma_load_3d(smem + (2 * st + 1) * TILE_BYTES, &tm_k, &full[st], 0, kt * BKV, b * p.heads + h);
@@ -283,70 +307,98 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   } else if (warp == 1) {
     constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
     for (int h = 0; h < p.heads; ++h) {
-      const int st = h & 1;
-      mbar_wait(&full[st], (h >> 1) & 1);
-      mbar_wait(&s_empty[st], ((h >> 1) & 1) ^ 1);
+      const int st = h % HM_STAGES, tb = h & 1;
+      mbar_wait(&full[st], (h / HM_STAGES) & 1);
+      mbar_wait(&s_empty[tb], ((h >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t q_base = smem_u32(smem + (2 * st) * TILE_BYTES), k_base = smem_u32(smem + (2 * st + 1) * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          mma_f16_ss(tmem + st * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
+          mma_f16_ss(tmem + tb * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
         tc_commit(&empty[st]);
-        tc_commit(&s_full[st]);
+        tc_commit(&s_full[tb]);
       }
       __syncwarp();
     }
   } else {
     const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;                 // which 64-column half of the tile this warp accumulates
     const int row = quad * 32 + lane;
     const int t = qt * BQ + row;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    float acc[128];
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + chalf * 64;
+    float acc[64];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    // softmax row statistics of all heads for this query tile -> smem once (keeps global-load latency off the head loop)
+    float2* ml_s = reinterpret_cast<float2*>(smem + HM_SMEM_TILES + 256 + BQ * HM_STAGE_LD * 4);
+    for (int i = threadIdx.x - 64; i < p.heads * BQ; i += HM_THREADS - 64) {
+      const int hh = i / BQ, r = i - hh * BQ, tt = qt * BQ + r;
+      float2 v = make_float2(0.f, 0.f);                  // rows >= T contribute exactly 0
+      if (tt < p.T) {
+        const size_t si = ((size_t)b * p.heads + hh) * p.T + tt;
+        v = make_float2(p.m[si], 1.f / p.l[si]);
+      }
+      ml_s[i] = v;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int h = 0; h < p.heads; ++h) {
       const int st = h & 1;
-      float mrow = 0.f, inv_l = 0.f;      // rows >= T contribute exactly 0
-      if (t < p.T) {
-        const size_t si = ((size_t)b * p.heads + h) * p.T + t;
-        mrow = p.m[si];
-        inv_l = 1.f / p.l[si];
-      }
+      const float2 mlv = ml_s[h * BQ + row];
+      const float mrow = mlv.x, inv_l = mlv.y;
       mbar_wait(&s_full[st], (h >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + st * 128 + c * 32, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          acc[c * 32 + i] = fmaf(exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mrow)), inv_l, acc[c * 32 + i]);
-      }
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(lane_addr + st * 128, v0);
+      tmem_ld_32x32(lane_addr + st * 128 + 32, v1);
+      tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (lane == 0) mbar_arrive(&s_empty[st]);       // S_h is in registers: the next head's MMA may overwrite the buffer
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = fmaf(ex2_approx(fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow)), inv_l, acc[i]);
+        acc[32 + i] = fmaf(ex2_approx(fmaf(__uint_as_float(v1[i]), p.scale_log2, -mrow)), inv_l, acc[32 + i]);
+      }
     }
     // stage through smem so the global stores are row-contiguous
     float* stage = reinterpret_cast<float*>(smem + HM_SMEM_TILES + 256);
     const float inv_h = 1.f / (float)p.heads;
-    asm volatile("bar.sync 1, 128;" ::: "memory");     // all 4 epilogue warps are past their last MMA-visible smem use
     float rs = 0.f;
 #pragma unroll
-    for (int i = 0; i < 128; ++i) {
-      const float v = (kt * BKV + i < p.T) ? acc[i] * inv_h : 0.f;
+    for (int i = 0; i < 64; ++i) {
+      const int c = chalf * 64 + i;
+      const float v = (kt * BKV + c < p.T) ? acc[i] * inv_h : 0.f;
       rs += v;
-      stage[row * HM_STAGE_LD + i] = v;
+      stage[row * HM_STAGE_LD + c] = v;
     }
-    if (p.rowsum_part && t < p.T) p.rowsum_part[((size_t)b * p.T + t) * p.ntile + kt] = rs;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* rs_s = reinterpret_cast<float*>(ml_s);          // the statistics are dead now: reuse for the two half-row sums
+    rs_s[chalf * BQ + row] = rs;                           // each thread's 64 values were added in a fixed order
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (p.rowsum_part && t < p.T && chalf == 0)
+      p.rowsum_part[((size_t)b * p.T + t) * p.ntile + kt] = rs_s[row] + rs_s[BQ + row];
     const int ncol = min(BKV, p.T - kt * BKV);
-    for (int r = (warp - 2); r < BQ; r += 4) {
+    for (int r = (warp - 2); r < BQ; r += 8) {
       const int tr = qt * BQ + r;
       if (tr >= p.T) break;
       float* dst = p.out + ((size_t)b * p.T + tr) * p.ld + kt * BKV;
       for (int c = lane; c < ncol; c += 32) dst[c] = stage[r * HM_STAGE_LD + c];
+    }
+    if (p.t_hi) {
+      // transposed tile for the roll-out GEMM (B operand, K-major): At[n = key][k = query], x = hi + lo in fp16
+      for (int c = (warp - 2); c < BKV; c += 8) {
+        const size_t o = ((size_t)b * p.ldt + kt * BKV + c) * p.ldt + qt * BQ;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r0 = half * 64 + 2 * lane;
+          const float v0 = stage[r0 * HM_STAGE_LD + c] * p.t_scale, v1 = stage[(r0 + 1) * HM_STAGE_LD + c] * p.t_scale;
+          const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+          const __half2 hi = __halves2half2(h0, h1);
+          const __half2 lo = __floats2half2_rn(v0 - __half2float(h0), v1 - __half2float(h1));
+          *reinterpret_cast<__half2*>(p.t_hi + o + r0) = hi;
+          *reinterpret_cast<__half2*>(p.t_lo + o + r0) = lo;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -392,8 +444,10 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
 
 // out [B,T,ld] fp32 (ld >= T), rowsum_part [B,T,ceil(T/128)] (may be null)
 extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
-                                float* rowsum_part, int B, int T, int heads, cudaStream_t stream) {
-  if (ld < T) return AS_ERR_BAD_ARG;
+                                float* rowsum_part, void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads,
+                                cudaStream_t stream) {
+  if (ld < T || heads > HM_MAX_HEADS) return AS_ERR_BAD_ARG;
+  if (t_hi && (!t_lo || ldt != (T + BKV - 1) / BKV * BKV)) return AS_ERR_BAD_ARG;
   CUtensorMap tm_q, tm_k;
   int r = encode_qk(&tm_q, q, B * heads, T);
   if (r) return r;
@@ -407,6 +461,7 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
   HmParams p;
   p.T = T; p.heads = heads; p.ld = ld; p.scale_log2 = (float)(0.125 * 1.4426950408889634);
   p.m = m; p.l = l; p.out = out; p.rowsum_part = rowsum_part; p.ntile = (T + BKV - 1) / BKV;
+  p.t_hi = (__half*)t_hi; p.t_lo = (__half*)t_lo; p.ldt = ldt; p.t_scale = t_scale;
   const int nt = (T + BQ - 1) / BQ;
   attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
   AS_LAUNCH_CHECK();

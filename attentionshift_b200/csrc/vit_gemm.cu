@@ -3,11 +3,12 @@
 // Reference ops replaced: nn.Linear qkv (models/vision_transformer.py:76), proj (:84), Mlp fc1/GELU/fc2 (:40-59)
 // plus the residual adds of Block.forward (:110-115).
 //
-// Structure (one CTA per SM, persistent over 128x256 output tiles):
+// Structure (one CTA per SM, persistent; thread-block clusters of 2 CTAs = one CTA pair per 256x256 output tile, each CTA
+// owning 128 rows of it):
 //   warp 0      : TMA producer  -- X and W tiles (64 halves = 128 B rows, SWIZZLE_128B) into a 4-stage smem ring
-//   warp 1      : MMA issuer    -- tcgen05.mma.kind::f16 (M128 N256 K16), fp32 accumulators in TMEM, 2 accumulator
+//   warp 1      : MMA issuer    -- tcgen05.mma.cta_group::2.kind::f16 (M256 N256 K16 across the pair), fp32 accumulators in TMEM, 2 accumulator
 //                                  buffers (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of i+1
-//   warps 2..5  : epilogue      -- tcgen05.ld 32x32b, bias / GELU / residual / QKV head split, vector stores
+//   warps 2..9  : epilogue      -- tcgen05.ld 32x32b, bias / GELU / residual / QKV head split, vector stores
 #include "common.cuh"
 
 using namespace asb;
@@ -18,12 +19,17 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 128 columns each)
 
 enum { EPI_F16 = 0, EPI_GELU_F16 = 1, EPI_RESID_F32 = 2, EPI_QKV = 3, EPI_F32 = 4 };
 
 struct GemmParams {
   int M, N, K, epi;
+  int batch;                 // independent problems; X rows / W rows / out are strided per batch
+  long long out_bstride;     // elements
+  long long resid_bstride;   // elements
+  int ldo;                   // row stride (elements) of out / resid
+  float alpha;               // scales the accumulator before bias / residual
   const float* bias;
   void* out;
   const float* resid;
@@ -33,7 +39,22 @@ struct GemmParams {
   int T, Tpad, heads;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), nn.GELU's exact form (VT:55).  erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the fp16 rounding of the stored activation); 14 instructions per element -- erff()
+// made the fc1 epilogue longer than its mainloop.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float z2 = ax * 0.84932180028801907f;               // sqrt(log2(e) / 2): exp(-z^2) = 2^(-z2^2)
+  const float e = fmaf(-poly * t, ex2_approx(-z2 * z2), 1.0f);   // erf(|x| / sqrt 2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), e, hx);                            // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
+}
 
 __device__ __forceinline__ void store_f16x32(__half* dst, const float* f) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -52,125 +73,196 @@ __device__ __forceinline__ void store_f16x32(__half* dst, const float* f) {
   }
 }
 
+template <int kPair>     // 2: a pair of CTAs (cluster of 2) drives ONE cta_group::2 MMA of shape 256x256; 1: stand-alone CTA, 128x256
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const GemmParams p) {
+  // Paired mode: each CTA stages its own 128 rows of X and its own 128 rows of W per k-block (32 KB instead of 48 KB), the
+  // tensor cores of the two SMs exchange the W halves, and every SM's shared memory sees 128 B/clk of TMA fills + MMA
+  // operand reads instead of 192 B/clk -- the single-CTA shape is shared-memory-bandwidth bound near 45% tensor utilisation.
+  constexpr int kStages = kPair == 2 ? 6 : 4;
+  constexpr int kBBytes = kPair == 2 ? B_BYTES / 2 : B_BYTES;
+  static_assert(kStages * (A_BYTES + kBBytes) + 1024 + 256 <= SMEM_BYTES, "smem budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint8_t* smem_b = smem + kStages * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * (A_BYTES + kBBytes));
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = kPair == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8 * kPair);   // the leader's MMA thread waits for the epilogue warps of BOTH CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (kPair == 2) tmem_alloc_2cta<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair == 2) cluster_sync_all();   // peer barriers / TMEM are set up before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cluster_id = blockIdx.x / kPair, n_clusters = gridDim.x / kPair;
 
   const int num_m = (p.M + BM - 1) / BM;
+  const int num_mp = (num_m + kPair - 1) / kPair;          // groups of row blocks, one block per CTA of the pair
   const int num_n = (p.N + BN - 1) / BN;
-  const int tiles = num_m * num_n;
+  const int tiles_per_batch = num_mp * num_n;
+  const int tiles = tiles_per_batch * p.batch;
   const int kblocks = p.K / BK;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = cluster_id; tile < tiles; tile += n_clusters) {
+        const int bi = tile / tiles_per_batch, tb = tile - bi * tiles_per_batch;
+        const int m_blk = kPair * (tb / num_n) + rank, n_blk = tb % num_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
-          tma_load_2d(smem_a + stage * A_BYTES, &tm_a, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * B_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kPair == 2) {
+            if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + kBBytes));     // both CTAs' boxes land on my barrier
+            tma_load_3d_2cta(smem_a + stage * A_BYTES, &tm_a, &full[stage], kb * BK, m_blk * BM, bi);
+            tma_load_3d_2cta(smem_b + stage * kBBytes, &tm_b, &full[stage], kb * BK, n_blk * BN + rank * (BN / 2), bi);
+          } else {
+            mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            tma_load_3d(smem_a + stage * A_BYTES, &tm_a, &full[stage], kb * BK, m_blk * BM, bi);
+            tma_load_3d(smem_b + stage * B_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN, bi);
+            tma_load_3d(smem_b + stage * B_BYTES + B_BYTES / 2, &tm_b, &full[stage], kb * BK, n_blk * BN + BN / 2, bi);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc(0, BM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full[stage], phase);
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc(0, BM * kPair, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < tiles; tile += n_clusters) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_base = smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t b_base = smem_u32(smem_b + stage * B_BYTES);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_base = smem_u32(smem_a + stage * A_BYTES);
+            const uint32_t b_base = smem_u32(smem_b + stage * kBBytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            mma_f16_ss(tmem_base + acc * BN, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32),
-                       idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (kPair == 2)
+                mma_f16_ss_2cta(tmem_base + acc * BN, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32),
+                                idesc, (kb | k) != 0);
+              else
+                mma_f16_ss(tmem_base + acc * BN, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32),
+                           idesc, (kb | k) != 0);
+            }
+            if (kPair == 2) {
+              tc_commit_2cta_mcast(&empty[stage], (uint16_t)3);            // frees the stage in both CTAs
+              if (kb == kblocks - 1) tc_commit_2cta_mcast(&tfull[acc], (uint16_t)3);
+            } else {
+              tc_commit(&empty[stage]);
+              if (kb == kblocks - 1) tc_commit(&tfull[acc]);
+            }
           }
-          tc_commit(&empty[stage]);
-          if (kb == kblocks - 1) tc_commit(&tfull[acc]);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int quad = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;   // which 128-column half of the accumulator this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     const int C = p.heads * 64;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = cluster_id; tile < tiles; tile += n_clusters) {
+      const int bi = tile / tiles_per_batch, tb = tile - bi * tiles_per_batch;
+      const int m_blk = kPair * (tb / num_n) + rank, n_blk = tb % num_n;
       const int m = m_blk * BM + quad * 32 + lane;
+      const int c_beg = chalf * (BN / 64), c_end = (chalf + 1) * (BN / 64);
+      const bool live = m < p.M;
+      // the residual does not depend on the MMA: fetch the first chunk before the accumulator is ready and always keep
+      // the next chunk's loads in flight (the K=768 GEMMs were bound by this load latency)
+      float4 rnext[8];
+      const float* rrow = nullptr;
+      if (p.epi == EPI_RESID_F32) {
+        rrow = p.resid + bi * p.resid_bstride + (size_t)(live ? m : 0) * p.ldo;
+        const int n0 = n_blk * BN + c_beg * 32;
+        if (live && n0 < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + n0) + i);
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       int b_idx = 0, t_idx = 0;
-      if (p.epi == EPI_QKV && m < p.M) { b_idx = m / p.T; t_idx = m - b_idx * p.T; }
+      if (p.epi == EPI_QKV && live) { b_idx = m / p.T; t_idx = m - b_idx * p.T; }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_beg; c < c_end; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-        tc_wait_ld();
         const int n0 = n_blk * BN + c * 32;
-        if (m < p.M && n0 < p.N) {
-          float f[32];
+        float4 rcur[8];
+        if (p.epi == EPI_RESID_F32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+          const int n1 = n0 + 32;
+          if (c + 1 < c_end && live && n1 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + n1) + i);
+          }
+        }
+        tc_wait_ld();
+        if (live && n0 < p.N) {
+          float f[32];
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+              f[4 * i] = fmaf(__uint_as_float(v[4 * i]), p.alpha, b4.x);
+              f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), p.alpha, b4.y);
+              f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), p.alpha, b4.z);
+              f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), p.alpha, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          }
           if (p.epi == EPI_F16) {
-            store_f16x32(reinterpret_cast<__half*>(p.out) + (size_t)m * p.N + n0, f);
+            store_f16x32(reinterpret_cast<__half*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0, f);
           } else if (p.epi == EPI_GELU_F16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-            store_f16x32(reinterpret_cast<__half*>(p.out) + (size_t)m * p.N + n0, f);
+            store_f16x32(reinterpret_cast<__half*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0, f);
           } else if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.N + n0);
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0);
             if (p.epi == EPI_RESID_F32) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)m * p.N + n0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float4 r = r4[i];
+                const float4 r = rcur[i];
                 o4[i] = make_float4(r.x + f[4 * i], r.y + f[4 * i + 1], r.z + f[4 * i + 2], r.w + f[4 * i + 3]);
               }
             } else {
@@ -195,37 +287,64 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kPair == 2) mbar_arrive_cluster(&tempty[acc], 0);     // the leader's MMA thread owns the accumulator hand-shake
+        else mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (kPair == 2) cluster_sync_all();   // nobody leaves (or frees TMEM) while the pair still works on shared state
+  if (warp == 1) {
+    if (kPair == 2) tmem_dealloc_2cta<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
-int launch_linear(const void* x, const void* w, const GemmParams& p, cudaStream_t stream) {
-  if (p.K % BK != 0 || p.M <= 0 || p.N <= 0 || (p.N % 32) != 0) return AS_ERR_BAD_ARG;
+int launch_linear(const void* x, const void* w, long long x_rows_per_batch, long long w_rows_per_batch, const GemmParams& p,
+                  cudaStream_t stream) {
+  if (p.K % BK != 0 || p.M <= 0 || p.N <= 0 || (p.N % 32) != 0 || p.batch < 1 || (p.ldo % 4) != 0) return AS_ERR_BAD_ARG;
   CUtensorMap tm_a, tm_b;
-  uint64_t dims_a[2] = {(uint64_t)p.K, (uint64_t)p.M}, str_a[1] = {(uint64_t)p.K * 2};
-  uint32_t box_a[2] = {BK, BM};
-  uint64_t dims_b[2] = {(uint64_t)p.K, (uint64_t)p.N}, str_b[1] = {(uint64_t)p.K * 2};
-  uint32_t box_b[2] = {BK, BN};
-  int r = as_encode_tmap(&tm_a, x, 2, 2, dims_a, str_a, box_a);
+  uint64_t dims_a[3] = {(uint64_t)p.K, (uint64_t)(p.batch > 1 ? x_rows_per_batch : p.M), (uint64_t)p.batch};
+  uint64_t str_a[2] = {(uint64_t)p.K * 2, (uint64_t)x_rows_per_batch * p.K * 2};
+  uint32_t box_a[3] = {BK, BM, 1};
+  uint64_t dims_b[3] = {(uint64_t)p.K, (uint64_t)(p.batch > 1 ? w_rows_per_batch : p.N), (uint64_t)p.batch};
+  uint64_t str_b[2] = {(uint64_t)p.K * 2, (uint64_t)w_rows_per_batch * p.K * 2};
+  uint32_t box_b[3] = {BK, BN / 2, 1};     // each CTA of the cluster fetches (and multicasts) half of the W tile
+  int r = as_encode_tmap(&tm_a, x, 2, 3, dims_a, str_a, box_a);
   if (r) return r;
-  r = as_encode_tmap(&tm_b, w, 2, 2, dims_b, str_b, box_b);
+  r = as_encode_tmap(&tm_b, w, 2, 3, dims_b, str_b, box_b);
   if (r) return r;
   static int num_sms = 0;
   if (!num_sms) {
     int dev;
     AS_CUDA(cudaGetDevice(&dev));
     AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    AS_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AS_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AS_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  linear_tcgen05_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  if (num_m == 1) {
+    const int tiles = num_n * p.batch;
+    linear_tcgen05_kernel<1><<<tiles < num_sms ? tiles : num_sms, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+  } else {
+    const int tiles = ((num_m + 1) / 2) * num_n * p.batch;       // cluster tiles
+    const int max_clusters = num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (tiles < max_clusters ? tiles : max_clusters));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AS_CUDA(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<2>, tm_a, tm_b, p));
+  }
   AS_LAUNCH_CHECK();
   return 0;
 }
@@ -239,7 +358,8 @@ extern "C" int as_linear_f16(const void* x_f16, const void* w_f16, const float* 
   if (mode == EPI_RESID_F32 && !resid) return AS_ERR_BAD_ARG;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.epi = mode; p.bias = bias; p.out = out; p.resid = resid; p.heads = 1;
-  return launch_linear(x_f16, w_f16, p, stream);
+  p.batch = 1; p.ldo = N; p.alpha = 1.f;
+  return launch_linear(x_f16, w_f16, M, N, p, stream);
 }
 
 // x [B*T, C] fp16, w [3C, C] fp16, bias [3C] -> q,k [B,h,T,64] fp16, vt [B,h,64,Tpad] fp16 (V transposed, K-major for P*V)
@@ -250,5 +370,19 @@ extern "C" int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float
   p.M = B * T; p.N = 3 * C; p.K = C; p.epi = EPI_QKV; p.bias = bias;
   p.q = (__half*)q; p.k = (__half*)k; p.vt = (__half*)vt; p.T = T; p.Tpad = Tpad; p.heads = heads;
   if (Tpad < T || (Tpad % 8) != 0) return AS_ERR_BAD_ARG;
-  return launch_linear(x_f16, w_f16, p, stream);
+  p.batch = 1; p.ldo = p.N; p.alpha = 1.f;
+  return launch_linear(x_f16, w_f16, p.M, p.N, p, stream);
+}
+
+// Batched fp32-output GEMM with scaling: out[b] = resid[b] + alpha * x[b] * w[b]^T   (resid may alias out, may be NULL)
+// x [batch, x_rows, K] f16 (M <= x_rows valid rows), w [batch, w_rows, K] f16 (N <= w_rows), out/resid [batch, M, ldo] f32.
+// Used by the roll-out slab: split-fp16 (hi + lo) operands give fp32-level accuracy on the fp16 tensor pipe.
+extern "C" int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M,
+                                int N, int K, int x_rows, int w_rows, int ldo, long long out_bstride, float alpha,
+                                cudaStream_t stream) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.epi = resid ? EPI_RESID_F32 : EPI_F32; p.bias = nullptr; p.out = out; p.resid = resid;
+  p.heads = 1; p.batch = batch; p.ldo = ldo; p.alpha = alpha; p.out_bstride = out_bstride; p.resid_bstride = out_bstride;
+  if (M > x_rows || N > w_rows) return AS_ERR_BAD_ARG;
+  return launch_linear(x_f16, w_f16, x_rows, w_rows, p, stream);
 }

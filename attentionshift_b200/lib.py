@@ -23,7 +23,10 @@ SIGNATURES = {
     'as_patch_im2col_f16': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'as_assemble_tokens': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'as_attn_headmean': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    'as_attn_headmean': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
+    'as_bgemm_f16_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _f, _vp]),
+    'as_rollout_tc_workspace': (_sz, [_i, _i, _i]),
+    'as_rollout_rows_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _sz, _vp]),
     'as_mean_shift_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_grid_seeds': (_i, [_vp, _f, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'as_mean_shift': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),

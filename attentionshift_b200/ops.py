@@ -79,18 +79,28 @@ def mhsa_fwd(q, k, vt, T):
     return o, m, l
 
 
-def attn_headmean(q, k, m, l, T, want_rowsum=True):
-    """VTD:236/242 attn.mean(1) recomputed from (q, k, m, l).  -> (mean [B,T,T] view of a row-padded buffer,
-    rowsum partials [B,T,ceil(T/128)] or None)."""
+T_SCALE = 16384.0     # 2^14: head-mean probabilities (<= 1) as split fp16 without touching the subnormal range
+
+
+def attn_headmean(q, k, m, l, T, want_rowsum=True, want_transposed=True):
+    """VTD:236/242 attn.mean(1) recomputed from (q, k, m, l).  -> mean [B,T,T] (view of a row-padded buffer).  The
+    tensor carries what the roll-out slab needs as attributes: ``_as_rowsum_part`` [B,T,ceil(T/128)] and, when
+    ``want_transposed``, ``_as_t16`` = (hi, lo) split-fp16 transposed maps [B,Tpad,Tpad] scaled by T_SCALE."""
     L = _l.load()
     B, heads = q.shape[0], q.shape[1]
     ld = (T + 127) // 128 * 128
     buf = torch.empty(B, T, ld, device=q.device, dtype=torch.float32)
     nt = (T + 127) // 128
     part = torch.empty(B, T, nt, device=q.device, dtype=torch.float32) if want_rowsum else None
-    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), B, T, heads,
-                                _l.stream_ptr()), 'as_attn_headmean')
-    return buf[:, :, :T], part
+    thi = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
+    tlo = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
+    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), _l.ptr(thi),
+                                _l.ptr(tlo), ld, T_SCALE, B, T, heads, _l.stream_ptr()), 'as_attn_headmean')
+    out = buf[:, :, :T]
+    out._as_rowsum_part = part
+    if want_transposed:
+        out._as_t16 = (thi, tlo)
+    return out, part
 
 
 def _feat_args(feats):

@@ -47,9 +47,15 @@ int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float* bias, voi
 int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T, int Tpad,
                 int heads, as_stream_t stream);
 
-/* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,ceil(T/128)] per-tile row sums (may be NULL). */
+/* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,ceil(T/128)] per-tile row sums (may be NULL).
+ * t_hi / t_lo (may be NULL): the TRANSPOSED map as a split-fp16 pair (x * t_scale = hi + lo), [B,ldt,ldt], ldt = T rounded
+ * up to 128, fully written (zero padded) -- the K-major B operand of the tensor-core roll-out. */
 int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld, float* rowsum_part,
-                     int B, int T, int heads, as_stream_t stream);
+                     void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads, as_stream_t stream);
+
+/* Batched f16 x f16 -> f32 GEMM on tcgen05: out[b] = resid[b] + alpha * x[b] w[b]^T (resid may alias out / be NULL). */
+int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M, int N, int K,
+                     int x_rows, int w_rows, int ldo, long long out_bstride, float alpha, as_stream_t stream);
 
 /* VT:110/114 LayerNorm (eps argument; 1e-6 at VT:146) with f16 output for the following GEMM. */
 int as_layernorm_f16(const float* x, const float* gamma, const float* beta, void* y_f16, int M, int C, float eps,
@@ -69,9 +75,16 @@ size_t as_rollout_workspace(int B, int T, int n_rows);
 int as_rollout_rows(const float* const* attn, const float* const* rowsum_part, int L, int B, int T, int ld, int ntile,
                     int n_rows, float* out, void* workspace, size_t workspace_bytes, as_stream_t stream);
 
+/* Same roll-out on the tensor cores: split-fp16 operands (3 MMAs per product, fp32-level accuracy).  t_hi / t_lo: HOST
+ * arrays of L device pointers to the transposed maps written by as_attn_headmean.  out [B,L,n_rows,ldt] (row stride ldt). */
+size_t as_rollout_tc_workspace(int B, int T, int ldt);
+int as_rollout_rows_tc(const float* const* attn, const void* const* t_hi, const void* const* t_lo,
+                       const float* const* rowsum_part, int L, int B, int T, int ld, int ldt, float t_scale, int ntile,
+                       int n_rows, float* out, void* workspace, size_t workspace_bytes, as_stream_t stream);
+
 /* ------------------------------------------------------------------ CAM -> pseudo box (RH:2272-2290, RH:60-116) */
 
-int as_cam_gather(const float* rows, const int* obj_img, const int* obj_pt, int L, int n_rows, int T, int N, int n_tot,
+int as_cam_gather(const float* rows, const int* obj_img, const int* obj_pt, int L, int n_rows, int row_stride, int N, int n_tot,
                   float* cams, as_stream_t stream);
 int as_cam_minmax(const float* lows, int n_maps, int hp, int wp, float* minmax, void* scratch, as_stream_t stream);
 size_t as_cam_bbox_workspace(int n_maps, int H, int W);

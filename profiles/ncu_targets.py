@@ -1,0 +1,29 @@
+"""Tiny driver for ncu: runs each hot kernel a couple of times at the cfg2 shapes (see profiles/run_ncu2.sh)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from attentionshift_b200 import ops
+dev = 'cuda'
+B, T, C, H = 8, 4197, 768, 12
+M = B * T
+Tpad = (T + 127) // 128 * 128
+x768 = (torch.randn(M, C, device=dev) * 0.5).half()
+w_qkv = (torch.randn(3 * C, C, device=dev) * 0.05).half()
+w_proj = (torch.randn(C, C, device=dev) * 0.05).half()
+w_fc1 = (torch.randn(4 * C, C, device=dev) * 0.05).half()
+b768, b2304, b3072 = torch.zeros(C, device=dev), torch.zeros(3 * C, device=dev), torch.zeros(4 * C, device=dev)
+resid = torch.randn(M, C, device=dev)
+which = sys.argv[1]
+for _ in range(2):
+    if which == 'proj':
+        ops.linear_f16(x768, w_proj, b768, ops.EPI_RESID_F32, resid=resid)
+    elif which == 'fc1':
+        ops.linear_f16(x768, w_fc1, b3072, ops.EPI_GELU_F16)
+    elif which == 'qkv':
+        ops.qkv_proj(x768, w_qkv, b2304, B, T, H, Tpad)
+    elif which in ('mhsa', 'headmean'):
+        q, k, vt = ops.qkv_proj(x768, w_qkv, b2304, B, T, H, Tpad)
+        o, m, l = ops.mhsa_fwd(q, k, vt, T)
+        if which == 'headmean':
+            ops.attn_headmean(q, k, m, l, T)
+torch.cuda.synchronize()

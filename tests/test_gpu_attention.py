@@ -30,3 +30,8 @@ def test_mhsa_and_headmean(B, heads, T):
     rmean = rattn.mean(1)                                               # VTD:236
     torch.testing.assert_close(mean, rmean, rtol=1e-3, atol=1e-6)       # north_star fp32 tolerance
     torch.testing.assert_close(part.sum(-1), rmean.sum(-1), rtol=1e-4, atol=1e-5)
+    # transposed split-fp16 copy (roll-out operand): hi + lo reproduces the fp32 map to ~2^-22 of T_SCALE
+    hi, lo = mean._as_t16
+    rec = (hi.float() + lo.float())[:, :T, :T].transpose(1, 2) / ops.T_SCALE
+    torch.testing.assert_close(rec, mean, rtol=2e-6, atol=1e-9)
+    assert hi[:, T:].abs().sum().item() == 0 and hi[:, :, T:].abs().sum().item() == 0

@@ -36,6 +36,28 @@ def test_rollout_rows_vs_oracle():
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-9)
 
 
+def test_rollout_rows_tensor_core_path():
+    """Roll-out fed by the head-mean kernel's own outputs (split-fp16 transposed maps) vs the fp32 oracle."""
+    from attentionshift_b200 import attention_shift as AS
+    from attentionshift_b200 import ops
+    torch.manual_seed(1)
+    B, heads, T, L, n_rows = 2, 2, 333, 4, 100
+    Tpad = (T + 127) // 128 * 128
+    maps = []
+    for _ in range(L):
+        q = (torch.randn(B, heads, T, 64, device=DEV) * 1.2).half()
+        k = (torch.randn(B, heads, T, 64, device=DEV) * 1.2).half()
+        vt = torch.zeros(B, heads, 64, Tpad, device=DEV, dtype=torch.float16)
+        _, m, l = ops.mhsa_fwd(q, k, vt, T)
+        maps.append(ops.attn_headmean(q, k, m, l, T)[0])
+    ref = O.rollout([a.cpu().contiguous() for a in maps])[:, :, -n_rows:, :]
+    out_tc = AS.rollout_rows(maps, n_rows, use_tensor_cores=True)
+    out_cc = AS.rollout_rows(maps, n_rows, use_tensor_cores=False)
+    assert out_tc.stride(2) == Tpad                     # really took the tensor-core path (padded row stride)
+    torch.testing.assert_close(out_cc.cpu(), ref, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(out_tc.cpu(), ref, rtol=1e-4, atol=1e-9)
+
+
 @pytest.mark.parametrize('hp,n_obj,seed', [(14, 2, 2), (28, 3, 5), (64, 3, 1)])
 def test_cam_boxes_bit_exact(hp, n_obj, seed):
     """A6/A7: integer outputs (kept-component mask, box extent) must be bit-exact on identical CAMs."""
