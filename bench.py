@@ -146,14 +146,11 @@ def count_launches(fn):
 
 
 def run_ours(args):
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
+    from attentionshift_b200 import parallel
+    rank, world, local = parallel.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
+    parallel.init('nccl', dev)
     cfg = dict(WORKLOAD)
     if args.small:
         cfg.update(batch=2, img=224, depth=2)
@@ -164,8 +161,7 @@ def run_ours(args):
     img_dev = img_host.to(dev)
 
     def barrier():
-        if world > 1:
-            torch.distributed.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
@@ -202,10 +198,7 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_dev, ms_e2e = t.tolist()
+    ms_dev, ms_e2e = parallel.max_over_ranks([ms_dev, ms_e2e], device=dev)     # the slowest rank defines the step
     n_ours, n_all = count_launches(lambda: one_step(bb, head, img_dev, inputs, False)) if rank == 0 else (None, None)
 
     if rank == 0:

@@ -1,0 +1,63 @@
+"""N > 1 path on CPU: two gloo ranks, the image axis is sharded with no data-path collective; only the timing reduction
+and the barrier use torch.distributed."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import torch
+    from attentionshift_b200 import parallel as P
+    rank, world, local = P.init(backend='gloo')
+    assert world == 2
+    mine = list(P.shard_images(13, rank, world))
+    # every rank works on its own images only; pretend the per-image result is a checksum
+    local_sum = float(sum(i * i for i in mine))
+    P.barrier()
+    tmax = P.max_over_ranks([10.0 + rank, 5.0 - rank])
+    tot = P.sum_over_ranks([local_sum, float(len(mine))])
+    if rank == 0:
+        print(json.dumps(dict(tmax=tmax, tot=tot, mine=mine)))
+    import torch.distributed as dist
+    dist.destroy_process_group()
+''')
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_two_gloo_ranks_shard_and_reduce(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % ROOT)
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    import json
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert res['tmax'] == [11.0, 5.0]                       # max over ranks of (10+rank, 5-rank)
+    assert res['tot'] == [float(sum(i * i for i in range(13))), 13.0]   # the two shards partition the 13 images
+    assert res['mine'] == list(range(7))
+
+
+def test_shards_partition_the_batch():
+    from attentionshift_b200.parallel import shard_images
+    for n in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            seen = [i for r in range(world) for i in shard_images(n, r, world)]
+            assert seen == list(range(n))
+            sizes = [len(shard_images(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
