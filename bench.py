@@ -147,6 +147,8 @@ def count_launches(fn):
 
 def run_ours(args):
     from attentionshift_b200 import parallel
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
+        os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line the driver parses
     rank, world, local = parallel.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
