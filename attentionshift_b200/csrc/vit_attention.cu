@@ -248,7 +248,8 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ head-mean probabilities
-constexpr int HM_THREADS = 320;   // TMA warp, MMA warp, 2 x 4 math warps (each quartet covers 64 of the 128 key columns)
+constexpr int HM_THREADS = 576;   // TMA warp, MMA warp, 4 x 4 math warps (each quartet covers 32 of the 128 key columns)
+constexpr int HM_MATH = HM_THREADS - 64;
 constexpr int HM_STAGES = 4;
 constexpr int HM_SMEM_TILES = 2 * HM_STAGES * TILE_BYTES;     // HM_STAGES x (Q_h, K_h)
 constexpr int HM_STAGE_LD = 129;                            // floats per staged output row (padded: conflict-free)
@@ -285,7 +286,7 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
     for (int i = 0; i < HM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], HM_MATH / 32); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -323,16 +324,16 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
   } else {
     const int quad = warp & 3;
-    const int chalf = (warp - 2) >> 2;                 // which 64-column half of the tile this warp accumulates
+    const int cslice = (warp - 2) >> 2;                // which 32-column slice of the tile this warp accumulates
     const int row = quad * 32 + lane;
     const int t = qt * BQ + row;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + chalf * 64;
-    float acc[64];
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + cslice * 32;
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     // softmax row statistics of all heads for this query tile -> smem once (keeps global-load latency off the head loop)
     float2* ml_s = reinterpret_cast<float2*>(smem + HM_SMEM_TILES + 256 + BQ * HM_STAGE_LD * 4);
-    for (int i = threadIdx.x - 64; i < p.heads * BQ; i += HM_THREADS - 64) {
+    for (int i = threadIdx.x - 64; i < p.heads * BQ; i += HM_MATH) {
       const int hh = i / BQ, r = i - hh * BQ, tt = qt * BQ + r;
       float2 v = make_float2(0.f, 0.f);                  // rows >= T contribute exactly 0
       if (tt < p.T) {
@@ -341,44 +342,41 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       ml_s[i] = v;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(HM_MATH) : "memory");
     for (int h = 0; h < p.heads; ++h) {
       const int st = h & 1;
       const float2 mlv = ml_s[h * BQ + row];
       const float mrow = mlv.x, inv_l = mlv.y;
       mbar_wait(&s_full[st], (h >> 1) & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32];
+      uint32_t v0[32];
       tmem_ld_32x32(lane_addr + st * 128, v0);
-      tmem_ld_32x32(lane_addr + st * 128 + 32, v1);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);       // S_h is in registers: the next head's MMA may overwrite the buffer
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 32; ++i)
         acc[i] = fmaf(ex2_approx(fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow)), inv_l, acc[i]);
-        acc[32 + i] = fmaf(ex2_approx(fmaf(__uint_as_float(v1[i]), p.scale_log2, -mrow)), inv_l, acc[32 + i]);
-      }
     }
     // stage through smem so the global stores are row-contiguous
     float* stage = reinterpret_cast<float*>(smem + HM_SMEM_TILES + 256);
     const float inv_h = 1.f / (float)p.heads;
     float rs = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      const int c = chalf * 64 + i;
+    for (int i = 0; i < 32; ++i) {
+      const int c = cslice * 32 + i;
       const float v = (kt * BKV + c < p.T) ? acc[i] * inv_h : 0.f;
       rs += v;
       stage[row * HM_STAGE_LD + c] = v;
     }
-    float* rs_s = reinterpret_cast<float*>(ml_s);          // the statistics are dead now: reuse for the two half-row sums
-    rs_s[chalf * BQ + row] = rs;                           // each thread's 64 values were added in a fixed order
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (p.rowsum_part && t < p.T && chalf == 0)
-      p.rowsum_part[((size_t)b * p.T + t) * p.ntile + kt] = rs_s[row] + rs_s[BQ + row];
+    float* rs_s = reinterpret_cast<float*>(ml_s);          // the statistics are dead now: reuse for the four slice sums
+    rs_s[cslice * BQ + row] = rs;                          // each thread's 32 values were added in a fixed order
+    asm volatile("bar.sync 1, %0;" ::"n"(HM_MATH) : "memory");
+    if (p.rowsum_part && t < p.T && cslice == 0)
+      p.rowsum_part[((size_t)b * p.T + t) * p.ntile + kt] = (rs_s[row] + rs_s[BQ + row]) + (rs_s[2 * BQ + row] + rs_s[3 * BQ + row]);
     const int ncol = min(BKV, p.T - kt * BKV);
-    for (int r = (warp - 2); r < BQ; r += 8) {
+    for (int r = (warp - 2); r < BQ; r += HM_MATH / 32) {
       const int tr = qt * BQ + r;
       if (tr >= p.T) break;
       float* dst = p.out + ((size_t)b * p.T + tr) * p.ld + kt * BKV;
@@ -386,7 +384,7 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     if (p.t_hi) {
       // transposed tile for the roll-out GEMM (B operand, K-major): At[n = key][k = query], x = hi + lo in fp16
-      for (int c = (warp - 2); c < BKV; c += 8) {
+      for (int c = (warp - 2); c < BKV; c += HM_MATH / 32) {
         const size_t o = ((size_t)b * p.ldt + kt * BKV + c) * p.ldt + qt * BQ;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
