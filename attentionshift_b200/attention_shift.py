@@ -99,6 +99,20 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+class _Pending:
+    """Device -> pinned-host copy enqueued now, awaited later: the host keeps launching kernels while the counts travel."""
+
+    def __init__(self, t):
+        self.host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self.host.copy_(t, non_blocking=True)
+        self.ev = torch.cuda.Event()
+        self.ev.record()
+
+    def get(self):
+        self.ev.synchronize()
+        return self.host
+
+
 def token_major(vit_feat):
     """[B,C,Hp,Wp] (the reference hands over a permuted view of last_feat, DET:77) or [B,N,C] -> [B,N,C] fp32 with
     unit channel stride, without a copy when the memory already is token-major."""
@@ -150,10 +164,9 @@ def rollout_rows(attns, n_rows, use_tensor_cores=True):
 
 
 # --------------------------------------------------------------------------------------------------- A6 / A7
-def cam_boxes(rows, obj_img, obj_pt, gt_points, hp, wp, cam_thr=0.2, area_ratio=0.5, want_keep_mask=False):
-    """RH:2272-2290: slice the matched point-token rows, (virtual) x16 bilinear, get_bbox_from_cam_fast per (layer, gt).
-    rows [B,L,n_rows,T]; obj_img/obj_pt int32 [n_tot]; gt_points [n_tot,2] (x,y).
-    -> (cams [L,n_tot,N] low-res, minmax [L,n_tot,2], boxes [L,n_tot,4], keep_mask or None)."""
+def cam_maps(rows, obj_img, obj_pt, hp, wp):
+    """RH:2272-2275 without the up-sampling: slice the matched point-token rows -> low-res CAMs [L,n_tot,N] and the
+    min / max [L,n_tot,2] their x16 bilinear up-sampling would have."""
     L = _l.load()
     B, nl, n_rows, T = rows.shape
     n_tot = obj_img.shape[0]
@@ -167,13 +180,29 @@ def cam_boxes(rows, obj_img, obj_pt, gt_points, hp, wp, cam_thr=0.2, area_ratio=
     mm = torch.empty(n_maps, 2, device=dev, dtype=torch.float32)
     scratch = torch.empty(n_maps * 2, device=dev, dtype=torch.int32)
     _l.check(L.as_cam_minmax(_p(cams), n_maps, hp, wp, _p(mm), _p(scratch), _sp()), 'as_cam_minmax')
+    return cams, mm.view(nl, n_tot, 2)
+
+
+def cam_bbox(cams, mm, gt_points, hp, wp, cam_thr=0.2, area_ratio=0.5, want_keep_mask=False):
+    """RH:60-116 get_bbox_from_cam_fast for every (layer, gt) map.  -> (boxes [L,n_tot,4], keep_mask or None)."""
+    L = _l.load()
+    nl, n_tot, N = cams.shape
+    dev = cams.device
+    n_maps = nl * n_tot
     boxes = torch.empty(n_maps, 4, device=dev, dtype=torch.float32)
     keep = torch.empty(n_maps, hp * 16, wp * 16, device=dev, dtype=torch.uint8) if want_keep_mask else None
     nbytes = L.as_cam_bbox_workspace(n_maps, hp * 16, wp * 16)
     ws = _ws(nbytes, dev)
     _l.check(L.as_cam_bbox(_p(cams), _p(mm), _p(gt_points), n_maps, n_tot, hp, wp, float(cam_thr), float(area_ratio),
                            _p(boxes), _p(keep), _p(ws), nbytes, _sp()), 'as_cam_bbox')
-    return cams, mm.view(nl, n_tot, 2), boxes.view(nl, n_tot, 4), keep
+    return boxes.view(nl, n_tot, 4), keep
+
+
+def cam_boxes(rows, obj_img, obj_pt, gt_points, hp, wp, cam_thr=0.2, area_ratio=0.5, want_keep_mask=False):
+    """RH:2272-2290: cam_maps + cam_bbox.  -> (cams [L,n_tot,N], minmax [L,n_tot,2], boxes [L,n_tot,4], keep_mask or None)."""
+    cams, mm = cam_maps(rows, obj_img, obj_pt, hp, wp)
+    boxes, keep = cam_bbox(cams, mm, gt_points, hp, wp, cam_thr, area_ratio, want_keep_mask)
+    return cams, mm, boxes, keep
 
 
 def cosine_maps(feats, grp_img, protos, clamp0=False):
@@ -206,20 +235,14 @@ class _Groups:
         self.d_img = torch.arange(self.G, dtype=torch.int32, device=dev)
 
 
-def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng, thr_pos=0.2, thr_neg=0.1,
-                 num_points=20, refine_times=2, obj_tau=0.85, mask_thr=0.6, want_bg=True, want_mask=True):
-    """RH:1000-1019 for every instance of the batch.
-    cam_low [n_tot,N] / cam_mm [n_tot,2]: selected-layer CAM (low-res) and min/max of its up-sampling; feats [n_img,N,C];
-    rois [n_tot,4]; gt_points [n_tot,2].  -> dict(map_fg, map_bg [n_tot,H,W], mask uint8, fg_low, bg_low [n_tot,N],
-    fg_feat [G,S,C] (rows 0..n of each group), pts [G,S,P,2], groups)."""
+def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=0.1):
+    """Candidate counting for the seed sampling (RH:343-352) + asynchronous copy of the counts to the host.  Issue this as
+    early as the selected CAMs exist: the counts cross PCIe while the GPU runs the connected-components stage."""
     L = _l.load()
-    dev = feats.device
-    n_img, N, C = feats.shape
-    n_tot = cam_low.shape[0]
-    H, W = hp * PATCH, wp * PATCH
+    dev = cam_low.device
+    H = hp * PATCH
     grp = _Groups(n_per_img, dev)
-    P = num_points
-    # ---- candidate counts: items ordered per image as the reference draws them: bg instances, fg instances, supplement
+    # items ordered per image as the reference draws them: bg instances, fg instances, supplement
     kinds, ia, ib, thr, item_img, item_slot = [], [], [], [], [], []
     for g, n in enumerate(grp.n):
         o0 = grp.first[g]
@@ -229,23 +252,47 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
             kinds.append(1); ia.append(o0 + j); ib.append(0); thr.append(thr_pos); item_img.append(g); item_slot.append(j)
         kinds.append(2); ia.append(o0); ib.append(o0 + n); thr.append(thr_neg); item_img.append(g); item_slot.append(n)
     n_items = len(kinds)
-    d_kind, d_a, d_b = _i32(kinds, dev), _i32(ia, dev), _i32(ib, dev)
+    st = dict(grp=grp, kinds=kinds, ia=ia, ib=ib, thr=thr, item_img=item_img, item_slot=item_slot, n_items=n_items,
+              d_kind=_i32(kinds, dev), d_a=_i32(ia, dev), d_b=_i32(ib, dev), cam_low=cam_low, cam_mm=cam_mm, hp=hp, wp=wp)
 
     def count(thr_list):
         d_thr = _f32(thr_list, dev)
         rc = torch.empty(n_items, H, device=dev, dtype=torch.int32)
-        _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), n_items, hp, wp, _p(rc),
-                                    _sp()), 'as_norm_rowcount')
-        return rc, d_thr, rc.sum(1).cpu().tolist()           # host sync (1)
+        _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(st['d_kind']), _p(st['d_a']), _p(st['d_b']), _p(d_thr), n_items,
+                                    hp, wp, _p(rc), _sp()), 'as_norm_rowcount')
+        return rc, d_thr, _Pending(rc.sum(1))
 
-    rowcnt, d_thr, totals = count(thr)
+    st['count'] = count
+    st['rowcnt'], st['d_thr'], st['pending'] = count(thr)
+    return st
+
+
+def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng, thr_pos=0.2, thr_neg=0.1,
+                 num_points=20, refine_times=2, obj_tau=0.85, mask_thr=0.6, want_bg=True, want_mask=True, begun=None):
+    """RH:1000-1019 for every instance of the batch.
+    cam_low [n_tot,N] / cam_mm [n_tot,2]: selected-layer CAM (low-res) and min/max of its up-sampling; feats [n_img,N,C];
+    rois [n_tot,4]; gt_points [n_tot,2].  -> dict(map_fg, map_bg [n_tot,H,W], mask uint8, fg_low, bg_low [n_tot,N],
+    fg_feat [G,S,C] (rows 0..n of each group), pts [G,S,P,2], groups).  ``begun``: state of refined_maps_begin."""
+    L = _l.load()
+    dev = feats.device
+    n_img, N, C = feats.shape
+    n_tot = cam_low.shape[0]
+    H, W = hp * PATCH, wp * PATCH
+    st = begun if begun is not None else refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos, thr_neg)
+    grp, kinds, ia, thr, item_img, item_slot, n_items = (st['grp'], st['kinds'], st['ia'], st['thr'], st['item_img'],
+                                                          st['item_slot'], st['n_items'])
+    d_kind, d_a, d_b = st['d_kind'], st['d_a'], st['d_b']
+    P = num_points
+    rowcnt, d_thr = st['rowcnt'], st['d_thr']
+    totals = st['pending'].get().tolist()                      # host sync (1) -- normally already satisfied
     # bg candidates too few -> the reference doubles the threshold until there are enough (RH:360-364)
     factor = [1.0] * n_items
     while any(kinds[i] != 1 and totals[i] < P for i in range(n_items)):
         for i in range(n_items):
             if kinds[i] != 1 and totals[i] < P:
                 factor[i] *= 2
-        rowcnt, d_thr, totals = count([t * f for t, f in zip(thr, factor)])
+        rowcnt, d_thr, pend = st['count']([t * f for t, f in zip(thr, factor)])
+        totals = pend.get().tolist()
     sel_item, sel_k, sel_dst = [], [], []
     pts_host = torch.zeros(grp.G, grp.S, P, 2, dtype=torch.int32)
     gtp = gt_points.detach().cpu()
@@ -301,8 +348,8 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
 
 
 # --------------------------------------------------------------------------------------------------- A12
-def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, num_gt=20, corr_size=21):
-    """RH:1980-1990 + RH:433-461.  -> (coords [n_tot,num_gt,2] fp32 (x,y), labels [n_tot,num_gt] bool)."""
+def mask_points_begin(map_fg, map_bg, rois, pos_thr=0.6, neg_thr=0.6, corr_size=21):
+    """Candidate maps + per-row counts of RH:433-443 and the asynchronous copy of the totals (and the boxes) to the host."""
     L = _l.load()
     dev = map_fg.device
     n_tot, H, W = map_fg.shape
@@ -312,8 +359,19 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
     ws = _ws(nbytes, dev)
     _l.check(L.as_mask_candidates(_p(map_fg), _p(map_bg), _p(rois), n_tot, H, W, float(pos_thr), float(neg_thr), int(corr_size),
                                   _p(pos), _p(rowcnt), _p(ws), nbytes, _sp()), 'as_mask_candidates')
-    totals = rowcnt.sum(1).cpu().tolist()                    # host sync (2)
-    rois_i = rois.detach().cpu().int()
+    return dict(pos=pos, rowcnt=rowcnt, ws=ws, map_bg=map_bg, rois=rois, neg_thr=neg_thr, pending=_Pending(rowcnt.sum(1)),
+                pending_rois=_Pending(rois.detach().int()), shape=(n_tot, H, W))
+
+
+def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, num_gt=20, corr_size=21, begun=None):
+    """RH:1980-1990 + RH:433-461.  -> (coords [n_tot,num_gt,2] fp32 (x,y), labels [n_tot,num_gt] bool)."""
+    L = _l.load()
+    dev = map_fg.device
+    st = begun if begun is not None else mask_points_begin(map_fg, map_bg, rois, pos_thr, neg_thr, corr_size)
+    n_tot, H, W = st['shape']
+    pos, rowcnt, ws = st['pos'], st['rowcnt'], st['ws']
+    totals = st['pending'].get().tolist()                    # host sync (2)
+    rois_i = st['pending_rois'].get()
     sel_obj, sel_kind, sel_k, sel_dst = [], [], [], []
     coords = torch.zeros(n_tot, num_gt, 2, dtype=torch.float32)
     labels = torch.zeros(n_tot, num_gt, dtype=torch.bool)
@@ -349,7 +407,7 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
 
 # --------------------------------------------------------------------------------------------------- A9 - A11
 def semantic_parts(map_fg, feats, obj_img, rois, hp, wp, pos_thr=0.6, n_shift=10, n_points=20, merge_thr=0.85,
-                   num_semantic_points=3, want_trace=False):
+                   num_semantic_points=3, want_trace=False, n_per_img=None):
     """RH:1995-2031 up to (not including) the ragged list assembly.  Everything stays on the device.
     -> dict(fg_low, seed_map, seed_tok, prot, sim, keep, merged, n_merged, part_maps, centers, valid, part_id, cfeat, trace)."""
     L = _l.load()
@@ -363,7 +421,7 @@ def semantic_parts(map_fg, feats, obj_img, rois, hp, wp, pos_thr=0.6, n_shift=10
     _l.check(L.as_erode_downsample(_p(map_fg), n_tot, H, W, float(pos_thr), 11, _p(fg_low), _p(seed_map), _sp()), 'as_erode_downsample')
     seed_tok, proto0 = ops.grid_seeds(seed_map, feats, obj_img, rois, wp, S, thr=0.35)
     prot, sim, trace = ops.mean_shift(proto0, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True,
-                                      want_trace=want_trace)
+                                      want_trace=want_trace, n_per_img=n_per_img)
     keep = torch.empty(n_tot, S, device=dev, dtype=torch.int32)
     _l.check(L.as_filter_seeds(_p(sim), _p(fg_low), n_tot, S, N, 0.85, _p(keep), None, _sp()), 'as_filter_seeds')
     merged = torch.empty(n_tot, S, C, device=dev, dtype=torch.float32)
@@ -379,13 +437,14 @@ def semantic_parts(map_fg, feats, obj_img, rois, hp, wp, pos_thr=0.6, n_shift=10
     _l.check(L.as_part_centers(_p(pmaps), _p(n_merged), _p(rois), _p(feats), feats.stride(0), _p(obj_img), n_tot, S, N, C, wp, KP,
                                _p(centers), _p(valid), _p(part_id), _p(cfeat), _p(stat), _sp()), 'as_part_centers')
     return dict(fg_low=fg_low, seed_map=seed_map, seed_tok=seed_tok, prot=prot, sim=sim, keep=keep, merged=merged,
-                n_merged=n_merged, part_maps=pmaps, centers=centers, valid=valid, part_id=part_id, cfeat=cfeat, trace=trace)
+                n_merged=n_merged, part_maps=pmaps, centers=centers, valid=valid, part_id=part_id, cfeat=cfeat, trace=trace,
+                pending=(_Pending(n_merged), _Pending(valid)))
 
 
 def assemble_parts(parts, n_per_img, gt_labels, hp, wp, num_max_keep=50):
     """Build the reference's ragged python structures (RH:244-262, RH:2024-2031) per image.  One host sync (3)."""
-    n_merged = parts['n_merged'].cpu().tolist()
-    valid = parts['valid'].cpu().bool()
+    n_merged = parts['pending'][0].get().tolist()            # host sync (3)
+    valid = parts['pending'][1].get().bool()
     out = []
     o = 0
     dev = parts['centers'].device

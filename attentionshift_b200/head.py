@@ -84,27 +84,34 @@ class AttnShiftRoIHead(nn.Module):
         labels = [gt_points_labels[i].to(dev) for i in range(B)]       # RH:2269 labels[i][pos_inds]: one label per matched GT
         # A5-A7
         rows = AS.rollout_rows(list(attns[-self.cam_layer:]), n_prop)
-        cams, mm, boxes, _ = AS.cam_boxes(rows, obj_img, obj_pt, pts, hp, wp, self.seed_thr, self.seed_multiple)
+        cams, mm = AS.cam_maps(rows, obj_img, obj_pt, hp, wp)
         n_tot = obj_img.shape[0]
+        ar = torch.arange(n_tot, device=dev)
+        if gt_index is not None:
+            gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index
+            gt_index = gt_index.to(dev).long()
+            # seed-candidate counts start their trip to the host now and overlap the connected-components stage
+            begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
+        boxes, _ = AS.cam_bbox(cams, mm, pts, hp, wp, self.seed_thr, self.seed_multiple)
         if gt_index is None:
             if self.mil_fn is None:
                 raise ValueError('seed_pseudo_gt needs gt_index= or a mil_fn (MIL head is outside the hot path)')
             gt_index = self.mil_fn(boxes.permute(1, 0, 2))
-        gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index
-        gt_index = gt_index.to(dev).long()
-        ar = torch.arange(n_tot, device=dev)
+            gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index
+            gt_index = gt_index.to(dev).long()
+            begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
         pseudo_boxes = boxes[gt_index, ar].contiguous()                # RH:2965-2967 gather of the chosen layer's box
-        cam_sel = cams[gt_index, ar].contiguous()
-        mm_sel = mm[gt_index, ar].contiguous()
-        # A8, A12, A13
-        rm = AS.refined_maps(cam_sel, mm_sel, feats, n_per_img, pseudo_boxes, pts, hp, wp, self.rng, refine_times=2,
-                             obj_tau=obj_tau, mask_thr=pos_mask_thr)
-        coords, plabels = AS.mask_points(rm['map_fg'], rm['map_bg'], pseudo_boxes, n_per_img, self.rng, pos_thr=pos_mask_thr,
-                                         neg_thr=neg_mask_thr, num_gt=num_mask_point_gt, corr_size=corr_size)
-        # A9-A11
+        # A8, A13
+        rm = AS.refined_maps(begun['cam_low'], begun['cam_mm'], feats, n_per_img, pseudo_boxes, pts, hp, wp, self.rng,
+                             refine_times=2, obj_tau=obj_tau, mask_thr=pos_mask_thr, begun=begun)
+        # A12 candidates are counted on the device while A9-A11 are enqueued; the host only then waits for the counts
+        mp = AS.mask_points_begin(rm['map_fg'], rm['map_bg'], pseudo_boxes, pos_thr=pos_mask_thr, neg_thr=neg_mask_thr,
+                                  corr_size=corr_size)
         parts = AS.semantic_parts(rm['map_fg'], feats, obj_img, pseudo_boxes, hp, wp, pos_thr=pos_mask_thr,
                                   n_shift=self.mean_shift_times_local, n_points=self.n_seeds,
-                                  num_semantic_points=self.num_semantic_points)
+                                  num_semantic_points=self.num_semantic_points, n_per_img=n_per_img)
+        coords, plabels = AS.mask_points(rm['map_fg'], rm['map_bg'], pseudo_boxes, n_per_img, self.rng, pos_thr=pos_mask_thr,
+                                         neg_thr=neg_mask_thr, num_gt=num_mask_point_gt, corr_size=corr_size, begun=mp)
         per_img = AS.assemble_parts(parts, n_per_img, labels, hp, wp)
         split = lambda t: list(t.split(n_per_img, dim=0))
         masks = [m.cpu().numpy() for m in split(rm['mask'])] if return_mask else split(rm['mask'])   # RH:2358 D2H hand-off

@@ -30,6 +30,8 @@ SIGNATURES = {
     'as_mean_shift_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_grid_seeds': (_i, [_vp, _f, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'as_mean_shift': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    'as_mean_shift_tc_workspace': (_sz, [_i, _i, _i, _i, _i, _i]),
+    'as_mean_shift_tc': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'as_rollout_workspace': (_sz, [_i, _i, _i]),

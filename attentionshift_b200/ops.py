@@ -128,17 +128,35 @@ def ctypes_ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True, want_trace=False):
-    """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C].
-    -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None)."""
+def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True, want_trace=False,
+               n_per_img=None, use_tensor_cores=True):
+    """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C]; instances grouped by image.
+    -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None).
+    C % 64 == 0 takes the tensor-core path (batched split-fp16 affinity GEMM); otherwise the fp32 CUDA-core kernels."""
     L = _l.load()
     n_tot, S, C = proto.shape
     n_img, N, _ = feats.shape
+    dev = proto.device
     proto = proto.contiguous().clone()
-    sim = torch.empty(n_tot, S, N, device=proto.device, dtype=torch.float32)
-    trace = torch.empty(n_shift, n_tot, N, device=proto.device, dtype=torch.int32) if want_trace else None
+    sim = torch.empty(n_tot, S, N, device=dev, dtype=torch.float32)
+    trace = torch.empty(n_shift, n_tot, N, device=dev, dtype=torch.int32) if want_trace else None
+    if n_per_img is None:
+        n_per_img = torch.bincount(obj_img.long(), minlength=n_img).cpu().tolist()      # host sync: pass n_per_img to avoid it
+    kmax = max(n_per_img) * S
+    if use_tensor_cores and C % 64 == 0 and kmax <= 256 and S * C * 4 <= 200 * 1024:
+        first = [0]
+        for k in n_per_img[:-1]:
+            first.append(first[-1] + k)
+        d_first = torch.tensor(first, dtype=torch.int32).to(dev, non_blocking=True)
+        d_nobj = torch.tensor(list(n_per_img), dtype=torch.int32).to(dev, non_blocking=True)
+        nbytes = L.as_mean_shift_tc_workspace(n_img, n_tot, S, N, C, kmax)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _l.check(L.as_mean_shift_tc(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(obj_img), _l.ptr(d_first),
+                                    _l.ptr(d_nobj), kmax, _l.ptr(rois), n_tot, S, _l.ptr(proto), _l.ptr(sim), n_shift, float(tau),
+                                    float(temp), int(clamp0), _l.ptr(trace), _l.ptr(ws), nbytes, _l.stream_ptr()), 'as_mean_shift_tc')
+        return proto, sim, trace
     nbytes = L.as_mean_shift_workspace(n_img, n_tot, S, N, C)
-    ws = torch.empty(nbytes, device=proto.device, dtype=torch.uint8)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     _l.check(L.as_mean_shift(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(obj_img), _l.ptr(rois),
                              n_tot, S, _l.ptr(proto), _l.ptr(sim), n_shift, float(tau), float(temp), int(clamp0),
                              _l.ptr(trace), _l.ptr(ws), nbytes, _l.stream_ptr()), 'as_mean_shift')

@@ -143,6 +143,14 @@ int as_mean_shift(const float* feats, long long feat_img_stride, int n_img, int 
                   double tau0, double temp, int clamp0, int* trace, void* workspace, size_t workspace_bytes,
                   as_stream_t stream);
 
+/* Tensor-core variant (C % 64 == 0): the affinity of all seeds of an image is one batched split-fp16 tcgen05 GEMM.
+ * Instances grouped by image: img_first / img_nobj device arrays [n_img]; kmax = max_i img_nobj[i] * S (host value). */
+size_t as_mean_shift_tc_workspace(int n_img, int n_tot, int S, int N, int C, int kmax);
+int as_mean_shift_tc(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
+                     const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois, int n_tot,
+                     int S, float* proto, float* sim, int n_shift, double tau0, double temp, int clamp0, int* trace,
+                     void* workspace, size_t workspace_bytes, as_stream_t stream);
+
 /* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
 
 int as_filter_seeds(const float* sim, const float* fg_low, int n_tot, int S, int N, float pos_thr, int* keep,

@@ -1,0 +1,67 @@
+"""AttnShiftRoIHead.seed_pseudo_gt end to end (roll-out -> CAM boxes -> refined maps -> mask points -> parts -> masks) on the
+device against the CPU oracle chain, fed with the oracle backbone's fp32 outputs so that only the attention-shift half
+is under test (the backbone has its own tests)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from attentionshift_b200.synthetic import vit_state_dict
+from oracle import attnshift as O
+from oracle import vit as V
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _iou(a, b):
+    a, b = a.bool(), b.bool()
+    return ((a & b).sum().item() + 1e-9) / ((a | b).sum().item() + 1e-9)
+
+
+def test_seed_pseudo_gt_vs_oracle():
+    from attentionshift_b200 import attention_shift as AS
+    from attentionshift_b200.registry import build_head
+    embed, heads, depth, img, n_pt = 64, 1, 7, 224, 12
+    hp = img // 16
+    sd = vit_state_dict(embed, depth, heads, img, n_point_tokens=n_pt, seed=4)
+    # sharpen the attention so CAMs have structure: scale the qkv weights up
+    for i in range(depth):
+        sd[f'blocks.{i}.attn.qkv.weight'] = sd[f'blocks.{i}.attn.qkv.weight'] * 12
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, img, img, generator=g)
+    ref = V.backbone_forward(x, sd, depth, heads, n_point_tokens=n_pt)
+    n_per = [2, 1]
+    pos_inds = [torch.tensor([3, 7]), torch.tensor([5])]
+    gt_points = [torch.tensor([[60., 80.], [150., 130.]]), torch.tensor([[100., 100.]])]
+    gt_index = [torch.tensor([6, 2]), torch.tensor([4])]
+    labels = [torch.tensor([1, 5]), torch.tensor([9])]
+    rng = AS.KeyedRng(11)
+    head = build_head(dict(type='AttnShiftRoIHead', bbox_head=dict(cam_layer=7, seed_thr=0.2, seed_multiple=0.5),
+                           mean_shift_times_local=3, n_seeds=20, num_semantic_points=3, rng=rng))
+    attns = [a.to(DEV) for a in ref['attns']]
+    vit_feat = ref['last_feat'][:, 1:].permute(0, 2, 1).unflatten(-1, (hp, hp)).to(DEV)        # DET:77 layout [B,C,Hp,Wp]
+    out = head.seed_pseudo_gt(None, None, None, None, None, vit_feat=vit_feat, point_cls=torch.zeros(2, n_pt, 20), attns=attns,
+                              gt_points=gt_points, gt_points_labels=labels, return_mask=True, pos_mask_thr=0.6, neg_mask_thr=0.1,
+                              num_mask_point_gt=10, corr_size=21, obj_tau=0.85, pos_inds=pos_inds, gt_index=gt_index)
+    assert set(out) >= {'pseudo_gt_labels', 'pseudo_gt_bboxes', 'mil_losses', 'best_attn_idx', 'map_cos_fg', 'mask_points_coords',
+                        'mask_points_labels', 'semantic_centers', 'semantic_centers_split', 'semantic_centers_feat_split',
+                        'semantic_centers_feat', 'num_parts', 'semantic_centers_org', 'pseudo_gt_masks', 'corres_gts',
+                        'inst_fg_feat', 'inst_bg_feat'}                    # RH:2398-2415
+    rows = O.rollout_rows(ref['attns'][-7:], n_pt)
+    for i, n in enumerate(n_per):
+        low, up = O.cams_from_rollout(rows[i], pos_inds[i], n_pt, hp, hp)
+        boxes = torch.stack([torch.cat([O.bbox_from_cam(up[l, j].clone(), gt_points[i][j], 0.2, 0.5, (img, img))[0] for j in range(n)])
+                             for l in range(7)])                            # [7, n, 4]
+        pb = boxes[gt_index[i], torch.arange(n)]
+        torch.testing.assert_close(out['pseudo_gt_bboxes'][i].cpu(), pb, rtol=0, atol=0)
+        o = O.attention_shift_image(up, gt_index[i], pb, ref['last_feat'][i, 1:].t().unflatten(-1, (hp, hp)).contiguous(),
+                                    gt_points[i], labels[i], pos_mask_thr=0.6, neg_mask_thr=0.1, num_mask_point_gt=10,
+                                    corr_size=21, obj_tau=0.85, mean_shift_times=3,
+                                    hook=lambda key: torch.manual_seed(rng.seed_for(key)), img=i)
+        torch.testing.assert_close(out['map_cos_fg'][i].cpu(), o['map_cos_fg'], rtol=1e-3, atol=1e-5)
+        assert torch.equal(out['mask_points_coords'][i].cpu(), o['mask_points_coords'])
+        assert torch.equal(out['mask_points_labels'][i].cpu(), o['mask_points_labels'])
+        for j in range(n):
+            assert _iou(torch.from_numpy(out['pseudo_gt_masks'][i][j]), o['pseudo_gt_masks'][j]) >= 0.999
+        assert out['num_parts'][i] == o['num_parts']
+        torch.testing.assert_close(out['semantic_centers_org'][0][i].cpu(), o['semantic_centers_org'][0], rtol=0, atol=0)

@@ -32,14 +32,17 @@ def _f64_margin_trace(prot, feats, n_shift, tau=0.1, temp=0.1):
     return out
 
 
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('hp,c,n_obj,S,n_shift,seed', [(14, 32, 2, 20, 5, 11), (28, 64, 3, 20, 10, 3), (28, 64, 3, 16, 5, 5),
-                                                       (20, 48, 5, 4, 2, 7), (64, 768, 3, 16, 5, 1)])
-def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed):
+                                                       (20, 48, 5, 4, 2, 7), (20, 64, 5, 4, 2, 7), (64, 768, 3, 16, 5, 1)])
+def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed, tc):
+    if tc and c % 64:
+        pytest.skip('tensor-core path needs C % 64 == 0')
     from attentionshift_b200 import ops
     sc = structured_scene(hp, hp, c, n_obj, seed=seed, noise=0.4)
     # foreground seed maps: the instance disks (owner labels) on the patch grid
     maps = torch.stack([((sc['labels'] == 2 * i + 1) | (sc['labels'] == 2 * i + 2)).float() for i in range(n_obj)])
-    if seed == 7:
+    if seed == 7:  # degenerate seed sets
         maps[1] = 0            # exercise the "no positive patch -> box centre" branch (RH:1799)
         maps[2, :] = 0
         maps[2, 3, 4] = 1      # and the repeat-fill branch (RH:1795)
@@ -53,7 +56,8 @@ def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed):
     tok, proto0 = ops.grid_seeds(maps.reshape(n_obj, -1).to(dev), feats, obj_img, rois, hp, S)
     sel = O.grid_seed_coords(maps, sc['rois'], 0.35, S)
     assert torch.equal(tok.cpu().long(), sel[..., 0] * hp + sel[..., 1])          # seed indices: bit-exact
-    prot, sim, tr = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, n_shift, want_trace=True)
+    prot, sim, tr = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, n_shift, want_trace=True, n_per_img=[n_obj],
+                                   use_tensor_cores=tc)
     torch.cuda.synchronize()
 
     # hard assignments: exact wherever the float64 margin is not at rounding level
