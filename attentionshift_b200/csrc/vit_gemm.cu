@@ -45,7 +45,9 @@ struct GemmParams {
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
   const float z = ax * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;   // rcp.approx (1 ulp): __frcp_rn expands to a Newton step plus a slow-path BRANCH per element, which serialised
+             // the 32 elements of a chunk (the epilogue took 4x the mainloop)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -114,7 +114,16 @@ class AttnShiftRoIHead(nn.Module):
                                          neg_thr=neg_mask_thr, num_gt=num_mask_point_gt, corr_size=corr_size, begun=mp)
         per_img = AS.assemble_parts(parts, n_per_img, labels, hp, wp)
         split = lambda t: list(t.split(n_per_img, dim=0))
-        masks = [m.cpu().numpy() for m in split(rm['mask'])] if return_mask else split(rm['mask'])   # RH:2358 D2H hand-off
+        if return_mask:                                         # RH:2358 hand-off: uint8 numpy masks on the host
+            m_dev = rm['mask']
+            # one pinned transfer (torch's caching host allocator recycles the block) instead of one pageable copy per
+            # image; the numpy arrays are views that keep the pinned tensor alive
+            m_host = torch.empty(m_dev.shape, dtype=torch.uint8, pin_memory=True)
+            m_host.copy_(m_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            masks = [m.numpy() for m in m_host.split(n_per_img, dim=0)]
+        else:
+            masks = split(rm['mask'])
         grp = rm['groups']
         fg_feat = [rm['centroid'][g, :n + 1].reshape(n + 1, -1, 1, 1) for g, n in enumerate(n_per_img)]
         bg_feat = [rm['centroid'][g, n + 1:2 * n + 1].reshape(n, -1, 1, 1) for g, n in enumerate(n_per_img)]
