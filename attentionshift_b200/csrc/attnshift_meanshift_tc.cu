@@ -19,7 +19,7 @@ extern "C" int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out
 namespace {
 
 constexpr float OP_SCALE = 1024.f;          // 2^10: normalised components (<= 1) as split fp16 away from the subnormals
-constexpr int CS_TOK = 256;                 // tokens per CTA in the column-statistics / Z / assign kernels
+constexpr int CS_TOK = 64;                  // tokens per CTA in the column-statistics / Z / assign kernels (small: many CTAs hide latency)
 constexpr int UP_TOK = 256;                 // tokens per CTA in the update kernel
 
 struct Box { int r0, r1, c0, c1; };
@@ -170,8 +170,8 @@ tc_zpart(const float* __restrict__ sim, ImgCtx c, const unsigned* __restrict__ c
   }
 }
 
-// hard assignment per (instance, token).  grid (tiles, n_img), one thread per token, the tile's rows staged in smem
-__global__ void __launch_bounds__(256)
+// hard assignment per (instance, token).  grid (tiles, n_img), CS_TOK threads = one per token, the tile's rows staged in smem
+__global__ void __launch_bounds__(CS_TOK)
 tc_assign(const float* __restrict__ sim, ImgCtx c, const float* __restrict__ stat, const float* __restrict__ z_part, int tiles,
           int* __restrict__ idx, float* __restrict__ wsel, int* __restrict__ trace) {
   extern __shared__ float sm[];
@@ -403,7 +403,7 @@ extern "C" int as_mean_shift_tc(const float* feats, long long feat_img_stride, i
     tc_fill_u32<<<(n_img * LD + 255) / 256, 256, 0, stream>>>(w.colmax, 0u, n_img * LD);
     tc_colstats<<<gt, 256, 0, stream>>>(w.sim, ctx, it ? w.idx : nullptr, w.colmax, w.dens);
     tc_zpart<<<gt, 256, 0, stream>>>(w.sim, ctx, w.colmax, w.dens, it == 0, tt0, (float)temp, w.zpart, w.stat);
-    tc_assign<<<gt, 256, asg_smem, stream>>>(w.sim, ctx, w.stat, w.zpart, w.tiles, w.idx, w.wsel,
+    tc_assign<<<gt, CS_TOK, asg_smem, stream>>>(w.sim, ctx, w.stat, w.zpart, w.tiles, w.idx, w.wsel,
                                             trace ? trace + (size_t)it * n_tot * N : nullptr);
     const dim3 gu(w.tiles_u, n_tot);
     if (J == 1) tc_update<1><<<gu, 256, upd_smem, stream>>>(feats, feat_img_stride, obj_img, rois, w.idx, w.wsel, N, C, hp, wp, S, w.part);
