@@ -228,11 +228,18 @@ def run_ours(args):
         att = fam.get('as_mhsa_fwd', {})
         flops_attn = 4.0 * T * T * C * B                      # SDPA part of F_attn, per launch (one layer, whole batch)
         roof = None
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_mhsa_traffic.json')      # dram bytes / launch from the committed ncu capture
+        if os.path.exists(tpath) and not args.small:
+            try:
+                traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+            except Exception:
+                traffic = None
         if att.get('n'):
             ach = flops_attn / (att['ms'] / att['n'] * 1e-3) / 1e12
             roof = dict(kernel='mhsa_fwd_kernel (tcgen05 flash attention, one launch = one layer x batch)', bound='tensor',
                         achieved=round(ach, 1), peak=pk['tf_sus'], unit='TFLOP/s', frac=round(ach / pk['tf_sus'], 4),
-                        traffic=None, peak_source=pk['src'] + ' sustained bf16 GEMM', share_of_step=round(att['ms'] / args.steps / ms_dev, 3))
+                        traffic=traffic, peak_source=pk['src'] + ' sustained bf16 GEMM', share_of_step=round(att['ms'] / args.steps / ms_dev, 3))
         msf = fam.get('as_mean_shift_tc') or fam.get('as_mean_shift', {})
         K = cfg['n_obj'] * cfg['seeds']
         b_alg = ((cfg['iters'] + 1) * N * C * 4 + K * N * 4 + 2 * K * C * 4) * B      # SURVEY 8d B_alg per image x images
