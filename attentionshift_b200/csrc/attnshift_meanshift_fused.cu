@@ -1,0 +1,705 @@
+// Attention-shift loop as ONE persistent cooperative kernel (as_mean_shift_fused).
+// Reference: cosine_shift_batch RH:830-854 + update_density_batch RH:882-908 (RH = stdroi_point_deform_attn_reppoints.py).
+//
+// Layout of the work: an image's N tokens are split over G = ceil(N/256) CTAs (one per SM, 256 tokens = two 128-row MMA
+// tiles each); the CTAs of an image form a group that synchronises through a global counter (4 group barriers per
+// iteration, no kernel launches, no host).  Token features are read as the split-fp16 pair written once by
+// tc_split_tokens (f^ * 2^10 = hi + lo; 4 bytes / element like fp32, and 100 MB at bs8 1024^2 stays L2 resident).
+//
+// Per iteration and CTA:
+//   A  affinity    TMA streams the CTA's token tiles (hi, lo) through a 3-stage ring and the image's seed tiles p^ (split
+//                  fp16, written by phase C of the previous iteration) through a 2-stage one; tcgen05 accumulates
+//                  hi.hi + hi.lo + lo.hi (M128 N64 K16) for both 128-token tiles in TMEM; epilogue -> box-masked
+//                  similarities in shared memory (kept for phase B), column max + density partials of the previous
+//                  assignment -> global
+//   -- group barrier --
+//   A2 statistics  every CTA combines the partials (fixed order): tau, logit max; partial softmax denominators -> global
+//   -- group barrier --
+//   B  assign      Z; per token and instance the arg-max seed of the softmax weight (first wins) and its weight; one warp
+//                  per instance compacts the contributing (in-box, non-zero weight) tokens into an ordered list
+//      update      token tiles are streamed again (64-row boxes, two 64 KB units in flight, started during assign);
+//                  thread = channel; f is rebuilt as (hi + lo) * |f| / 2^10; listed tokens are fetched 8 at a time;
+//                  run-length accumulation in registers, flushed to a shared-memory accumulator [64 seeds][256 channels]
+//                  only when the assigned seed changes; partials -> global
+//   -- group barrier --
+//   C  reduce      ordered sum of the G partials -> new prototypes, normalised split-fp16 copy p^ for the next affinity
+//                  (generic stores, fence.proxy.async + the group barrier make them visible to the other CTAs' TMA)
+//   -- group barrier --
+// and one more affinity pass (unmasked) for the returned similarity maps.  All reductions are ordered: deterministic.
+#include "common.cuh"
+#include <float.h>
+
+using namespace asb;
+
+namespace {
+
+constexpr int TOK = 256;                 // tokens per CTA
+constexpr int LDK = 64;                  // seed columns per image (n_obj * S <= 64)
+constexpr int MAXOBJ = 8;
+constexpr int SIM_LD = LDK + 1;
+constexpr int A_STAGE = 32768;           // hi 16 KB + lo 16 KB of a [128 x 64] fp16 tile
+constexpr int B_TILE = 16384;            // hi 8 KB + lo 8 KB of a [64 x 64] seed tile
+constexpr int RING = 3 * A_STAGE + 2 * B_TILE;     // 128 KB: 3 A stages + 2 B tiles (phase A) = 2 units of 64 KB (phase B)
+constexpr int FUSED_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 workers
+constexpr float OP_SCALE = 1024.f;
+
+struct Box { int r0, r1, c0, c1; };
+__device__ __forceinline__ Box patch_box(const float* roi, int hp, int wp) {   // box2mask(rois // 16), RH:303-309
+  Box b;
+  b.c0 = (int)floorf(roi[0] / 16.f); b.r0 = (int)floorf(roi[1] / 16.f);
+  b.c1 = (int)(floorf(roi[2] / 16.f) + 1.f); b.r1 = (int)(floorf(roi[3] / 16.f) + 1.f);
+  b.c0 = max(0, min(b.c0, wp)); b.c1 = max(0, min(b.c1, wp));
+  b.r0 = max(0, min(b.r0, hp)); b.r1 = max(0, min(b.r1, hp));
+  return b;
+}
+__device__ __forceinline__ bool in_box(const Box& b, int n, int wp) {
+  const int r = n / wp, c = n - r * wp;
+  return r >= b.r0 && r < b.r1 && c >= b.c0 && c < b.c1;
+}
+
+struct FusedParams {
+  int n_img, N, C, hp, wp, S, G, n_shift, clamp0;
+  float tt0, temp;
+  const int* img_first; const int* img_nobj; const float* rois;
+  const float* den;            // [n_img][N]   |f| (clamped at 1e-8)
+  float* proto;                // [n_tot][S][C] in/out
+  __half* phat_hi;             // [n_img][LDK][C] normalised seeds * 2^10, split fp16 (scratch; read back through TMA)
+  __half* phat_lo;
+  float* sim_out;              // [n_tot][S][N]
+  int* trace;                  // [n_shift][n_tot][N] or null
+  int n_tot;
+  float* colmax_part;          // [n_img][G][LDK]
+  float* dens_part;            // [n_img][G][LDK][2]
+  float* z_part;               // [n_img][G][LDK]
+  float* proto_part;           // [n_img][G][LDK][C]
+  unsigned* bar;               // [n_img] monotonic group-barrier counters
+  unsigned long long* dbg;     // optional [grid][16] accumulated ns per phase (as_mean_shift_fused_debug)
+};
+
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const uint64_t t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// byte offset of element (row, col) inside a K-major [rows x 64 halves] tile with the 128-byte swizzle
+__device__ __forceinline__ int sw128(int row, int col) { return row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1); }
+
+// ordered sum of G strided partials, loads issued in batches of 8 so that their latencies overlap
+__device__ __forceinline__ float sum_partials(const float* base, size_t stride, int G) {
+  float acc = 0.f;
+  for (int g0 = 0; g0 < G; g0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (g0 + i < G) ? __ldcg(base + (size_t)(g0 + i) * stride) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += v[i];
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64,
+                        const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_plo,
+                        const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;                                       // RING bytes
+  float* sims_s = reinterpret_cast<float*>(smem + RING);      // [TOK][SIM_LD]; aliased by the update accumulator [64][256]
+  float* acc_s = sims_s;
+  uint8_t* misc = smem + RING + TOK * SIM_LD * 4;
+  float* w_s = reinterpret_cast<float*>(misc);                // [MAXOBJ][TOK] weight of the assigned seed (0 outside the box)
+  float* lw_s = w_s + MAXOBJ * TOK;                           // [MAXOBJ][TOK] listed weights x |f| / 2^10
+  uint32_t* list_s = reinterpret_cast<uint32_t*>(lw_s + MAXOBJ * TOK);     // [MAXOBJ][TOK] listed tokens: tile offset | row << 13
+  float* den_s = reinterpret_cast<float*>(list_s + MAXOBJ * TOK);          // [TOK]
+  float* red_s = den_s + TOK;                                 // [256][3]
+  float* st_s = red_s + 256 * 3;                              // [LDK][4] 1/tt, column max, 1/Z, tau
+  int* ustart_s = reinterpret_cast<int*>(st_s + LDK * 4);     // [2][MAXOBJ][5] list offsets at the 64-token unit borders
+  int8_t* idx_s = reinterpret_cast<int8_t*>(ustart_s + 2 * MAXOBJ * 5);    // [MAXOBJ][TOK] assigned seed of the previous iteration
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + MAXOBJ * TOK);
+  bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~(uintptr_t)7);
+  uint64_t* a_full = bars;           // 3
+  uint64_t* a_empty = bars + 3;      // 3
+  uint64_t* b_full = bars + 6;       // 2
+  uint64_t* b_empty = bars + 8;      // 2
+  uint64_t* acc_full = bars + 10;    // 1
+  uint64_t* u_full = bars + 12;      // 2 (phase B units)
+  uint64_t* u_empty = bars + 14;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wt = threadIdx.x - 64;                            // worker thread id 0..255 (negative for warps 0, 1)
+  const int groups = gridDim.x / p.G;
+  const int grp = blockIdx.x / p.G, q = blockIdx.x % p.G;     // group id, rank inside the group
+  const int kblocks = p.C / 64;
+  const int chunks = (p.C + 255) / 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64);
+    tma_prefetch_desc(&tm_phi); tma_prefetch_desc(&tm_plo);
+    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+      mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // pipeline state that survives across passes / images (registers of the respective warps)
+  int a_stage = 0; uint32_t a_phase = 0;        // producer + MMA: A ring
+  uint32_t bcount = 0;                          // producer + MMA: B tile uses so far
+  uint32_t acount = 0;                          // workers: affinity passes so far
+  uint32_t ucount = 0;                          // producer + workers: phase B units so far
+
+  uint64_t t_prev = global_timer_ns();
+  auto mark = [&](int k) {
+    if (p.dbg && wt == 0) { const uint64_t t = global_timer_ns(); p.dbg[blockIdx.x * 16 + k] += t - t_prev; t_prev = t; }
+  };
+  if (grp >= groups) {                          // surplus CTAs (grid not a multiple of G): nothing to do
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<128>(tmem);
+    return;
+  }
+
+  for (int img = grp; img < p.n_img; img += groups) {
+    const int nobj = p.img_nobj[img], o0 = p.img_first[img];
+    const int kb_cols = nobj * p.S;
+    // the CTA's 256 tokens are four 64-token units taken round-robin over the group (unit u of CTA q = global unit u*G + q):
+    // every CTA sees all parts of the image, so box-shaped instance masks load the CTAs of a group evenly
+    auto tok = [&](int tl) { return ((tl >> 6) * p.G + q) * 64 + (tl & 63); };
+    unsigned* ctr = p.bar + img;
+    unsigned bar_target = 0;
+    if (wt >= 0) {
+      const int n = tok(wt);
+      den_s[wt] = n < p.N ? p.den[(size_t)img * p.N + n] : 1.f;
+      for (int j = 0; j < MAXOBJ; ++j) { idx_s[j * TOK + wt] = -1; w_s[j * TOK + wt] = 0.f; }
+    }
+    // new prototypes (ordered sum of the group's partials) and their normalised split-fp16 copy, rows q, q+G, ...
+    auto phase_c = [&](bool from_partials) {
+      if (wt >= 0) {
+        for (int r0 = q; r0 < kb_cols; r0 += 4 * p.G) {       // four rows at a time: their partial loads overlap
+          float v[4][4], ss[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[i][e] = 0.f;
+          if (from_partials) {
+            // ordered sum over the group's partials; the loads of all (row, channel) pairs of a step are in flight together
+            for (int g0 = 0; g0 < p.G; g0 += 4) {
+              float t[4][4][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                  for (int gg = 0; gg < 4; ++gg) {
+                    const int r = r0 + i * p.G, c = wt + e * 256, g = g0 + gg;
+                    t[i][e][gg] = (r < kb_cols && c < p.C && g < p.G)
+                                      ? __ldcg(p.proto_part + (((size_t)img * p.G + g) * LDK + r) * p.C + c) : 0.f;
+                  }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                  for (int gg = 0; gg < 4; ++gg) v[i][e] += t[i][e][gg];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int r = r0 + i * p.G, c = wt + e * 256;
+                if (r < kb_cols && c < p.C) v[i][e] = p.proto[((size_t)o0 * p.S + r) * p.C + c];
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ss[i] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ss[i] += v[i][e] * v[i][e];
+          }
+          if (from_partials) {                                // stores only after every partial load has been issued
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int r = r0 + i * p.G, c = wt + e * 256;
+                if (r < kb_cols && c < p.C) p.proto[((size_t)o0 * p.S + r) * p.C + c] = v[i][e];
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ss[i] = warp_sum(ss[i]);
+            if (lane == 0) red_s[i * 8 + warp - 2] = ss[i];
+          }
+          workers_sync();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i * p.G;
+            float tot = 0.f;
+            for (int k = 0; k < 8; ++k) tot += red_s[i * 8 + k];
+            const float nrm = fmaxf(sqrtf(tot), 1e-8f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = wt + e * 256;
+              if (r < kb_cols && c < p.C) {
+                const float x = v[i][e] / nrm * OP_SCALE;
+                const __half h = __float2half_rn(x);
+                const size_t o = ((size_t)img * LDK + r) * p.C + c;
+                p.phat_hi[o] = h;
+                p.phat_lo[o] = __float2half_rn(x - __half2float(h));
+              }
+            }
+          }
+          workers_sync();
+        }
+        fence_proxy_async_all();                              // the next reader of phat_hi/lo is another CTA's TMA
+      }
+    };
+    phase_c(false);
+    bar_target += p.G;
+    group_barrier(ctr, bar_target);
+    mark(0);
+
+    for (int it = 0; it <= p.n_shift; ++it) {
+      const bool last = (it == p.n_shift);                    // extra pass: unmasked similarities for the output
+      // ================================================================ phase A: affinity
+      if (warp == 0) {
+        if (lane == 0) {
+          fence_proxy_async_all();
+          for (int kb = 0; kb < kblocks; ++kb) {
+            const uint32_t bb = bcount & 1;
+            mbar_wait(&b_empty[bb], ((bcount >> 1) & 1) ^ 1);
+            mbar_expect_tx(&b_full[bb], B_TILE);
+            tma_load_3d(ring + 3 * A_STAGE + bb * B_TILE, &tm_phi, &b_full[bb], kb * 64, 0, img);
+            tma_load_3d(ring + 3 * A_STAGE + bb * B_TILE + 8192, &tm_plo, &b_full[bb], kb * 64, 0, img);
+            ++bcount;
+            for (int mt = 0; mt < 2; ++mt) {
+              mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+              mbar_expect_tx(&a_full[a_stage], A_STAGE);
+              for (int h = 0; h < 2; ++h) {                   // a 128-row operand tile = two 64-token units
+                const int row0 = ((2 * mt + h) * p.G + q) * 64;
+                tma_load_3d(ring + a_stage * A_STAGE + h * 8192, &tm_hi64, &a_full[a_stage], kb * 64, row0, img);
+                tma_load_3d(ring + a_stage * A_STAGE + 16384 + h * 8192, &tm_lo64, &a_full[a_stage], kb * 64, row0, img);
+              }
+              if (++a_stage == 3) { a_stage = 0; a_phase ^= 1; }
+            }
+          }
+        }
+      } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc(0, 128, LDK);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const uint32_t bb = bcount & 1;
+          mbar_wait(&b_full[bb], (bcount >> 1) & 1);
+          for (int mt = 0; mt < 2; ++mt) {
+            mbar_wait(&a_full[a_stage], a_phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_hi = smem_u32(ring + a_stage * A_STAGE), a_lo = a_hi + 16384;
+              const uint32_t b_hi = smem_u32(ring + 3 * A_STAGE + bb * B_TILE), b_lo = b_hi + 8192;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_f16_ss(tmem + mt * LDK, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, (kb | k) != 0);
+                mma_f16_ss(tmem + mt * LDK, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1);
+                mma_f16_ss(tmem + mt * LDK, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1);
+              }
+              tc_commit(&a_empty[a_stage]);
+              if (mt == 1) tc_commit(&b_empty[bb]);
+              if (mt == 1 && kb == kblocks - 1) tc_commit(acc_full);
+            }
+            __syncwarp();
+            if (++a_stage == 3) { a_stage = 0; a_phase ^= 1; }
+          }
+          ++bcount;
+        }
+      } else {
+        // ---- epilogue: TMEM -> box-masked similarities in shared memory (token-major)
+        {
+          const int quad = warp & 3, mt = (warp - 2) >> 2;
+          const int tl = mt * 128 + quad * 32 + lane;
+          const int n = tok(tl);
+          unsigned inmask = 0;                                // bit j: token inside instance j's box (all ones on the last pass)
+          if (n < p.N)
+            for (int j = 0; j < nobj; ++j)
+              if (last || in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n, p.wp)) inmask |= 1u << j;
+          mbar_wait(acc_full, acount & 1);
+          tc_fence_after();
+          mark(10);
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK, v0);
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK + 32, v1);
+          tc_wait_ld();
+          const float alpha = 1.f / (OP_SCALE * OP_SCALE);
+          float* row = sims_s + tl * SIM_LD;
+          int j = 0, s = 0;
+#pragma unroll
+          for (int col = 0; col < LDK; ++col) {
+            const float raw = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]);
+            row[col] = (col < kb_cols && ((inmask >> j) & 1u)) ? raw * alpha : 0.f;
+            if (++s == p.S) { s = 0; ++j; }
+          }
+          tc_fence_before();
+        }
+        ++acount;
+        workers_sync();
+        if (last) {
+          // returned maps [o][s][n]: one coalesced row of this CTA's tokens per seed
+          const int n = tok(wt);
+          if (n < p.N)
+            for (int col = 0; col < kb_cols; ++col) {
+              float v = sims_s[wt * SIM_LD + col];
+              if (p.clamp0) v = fmaxf(v, 0.f);
+              p.sim_out[((size_t)o0 * p.S + col) * p.N + n] = v;
+            }
+        } else {
+          // column statistics over this CTA's tokens: max, density partials of the previous assignment
+          const int col = wt & 63, g4 = wt >> 6;
+          float mx = -FLT_MAX, sv = 0.f, cv = 0.f;
+          if (col < kb_cols) {
+            const int j = col / p.S, s = col - j * p.S;
+#pragma unroll 8
+            for (int t = g4; t < TOK; t += 4) {
+              const bool ok = tok(t) < p.N;
+              const float v = sims_s[t * SIM_LD + col];
+              mx = ok ? fmaxf(mx, v) : mx;
+              const bool hit = ok && it > 0 && idx_s[j * TOK + t] == s;
+              sv += hit ? v : 0.f; cv += hit ? 1.f : 0.f;
+            }
+          }
+          red_s[wt * 3] = mx; red_s[wt * 3 + 1] = sv; red_s[wt * 3 + 2] = cv;
+          workers_sync();
+          if (g4 == 0 && col < kb_cols) {
+            for (int g = 1; g < 4; ++g) { mx = fmaxf(mx, red_s[(g * 64 + col) * 3]); sv += red_s[(g * 64 + col) * 3 + 1]; cv += red_s[(g * 64 + col) * 3 + 2]; }
+            const size_t pi = ((size_t)img * p.G + q) * LDK + col;
+            p.colmax_part[pi] = mx; p.dens_part[pi * 2] = sv; p.dens_part[pi * 2 + 1] = cv;
+          }
+        }
+      }
+      mark(1);
+      if (last) break;
+      bar_target += p.G;
+      group_barrier(ctr, bar_target);
+      mark(2);
+      // ================================================================ phase A2: per-seed statistics, partial Z
+      if (wt >= 0) {
+        const int col = wt & 63, g4 = wt >> 6;
+        if (g4 == 0 && col < kb_cols) {
+          const size_t p0 = (size_t)img * p.G * LDK + col;
+          float mx = -FLT_MAX;
+          for (int g0 = 0; g0 < p.G; g0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (g0 + i < p.G) ? __ldcg(p.colmax_part + p0 + (size_t)(g0 + i) * LDK) : -FLT_MAX;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+          }
+          float tt, tau = 0.f;
+          if (it == 0) tt = p.tt0;
+          else {
+            const float tot = sum_partials(p.dens_part + p0 * 2, (size_t)LDK * 2, p.G);
+            const float cnt = sum_partials(p.dens_part + p0 * 2 + 1, (size_t)LDK * 2, p.G);
+            tau = fmaxf(1.f - (cnt >= 1.f ? tot / cnt : 0.f), 1e-10f);       // RH:883-885, 908
+            tt = p.temp * tau;
+          }
+          st_s[col * 4] = 1.f / tt; st_s[col * 4 + 1] = mx; st_s[col * 4 + 3] = tau;
+        }
+        workers_sync();
+        float z = 0.f;
+        if (col < kb_cols) {
+          // logit - max logit as (v - max) / tt: exactly 0 at the maximum even when tt is ~1e-11 (tau clamped at 1e-10)
+          const float inv_tt = st_s[col * 4], cmax = st_s[col * 4 + 1];
+#pragma unroll 8
+          for (int t = g4; t < TOK; t += 4) {
+            const float e = expf((sims_s[t * SIM_LD + col] - cmax) * inv_tt);
+            z += tok(t) < p.N ? e : 0.f;
+          }
+        }
+        red_s[wt] = z;
+        workers_sync();
+        if (g4 == 0 && col < kb_cols) {
+          for (int g = 1; g < 4; ++g) z += red_s[g * 64 + col];
+          p.z_part[((size_t)img * p.G + q) * LDK + col] = z;
+        }
+      }
+      mark(3);
+      bar_target += p.G;
+      group_barrier(ctr, bar_target);
+      mark(4);
+      // ================================================================ phase B: assign + update
+      if (warp == 0) {
+        if (lane == 0) {                                      // the ring is free: the update's token tiles start streaming now
+          for (int cc = 0; cc < chunks; ++cc)
+            for (int rb = 0; rb < 4; ++rb) {
+              const uint32_t ub = ucount & 1;
+              mbar_wait(&u_empty[ub], ((ucount >> 1) & 1) ^ 1);
+              const int nk = min(4, kblocks - cc * 4);
+              mbar_expect_tx(&u_full[ub], nk * 16384);
+              for (int k4 = 0; k4 < nk; ++k4) {
+                tma_load_3d(ring + ub * 65536 + k4 * 16384, &tm_hi64, &u_full[ub], (cc * 4 + k4) * 64, (rb * p.G + q) * 64, img);
+                tma_load_3d(ring + ub * 65536 + k4 * 16384 + 8192, &tm_lo64, &u_full[ub], (cc * 4 + k4) * 64, (rb * p.G + q) * 64, img);
+              }
+              ++ucount;
+            }
+        }
+      } else if (wt >= 0) {
+        if (wt < kb_cols) st_s[wt * 4 + 2] = 1.f / sum_partials(p.z_part + (size_t)img * p.G * LDK + wt, LDK, p.G);    // fixed order
+        workers_sync();
+        {
+          const int n = tok(wt);
+          const float* row = sims_s + wt * SIM_LD;
+          for (int j = 0; j < nobj; ++j) {
+            float best = -1.f;
+            int bi = 0;
+            for (int s = 0; s < p.S; s += 4) {                // four independent exp chains in flight
+              float w4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int col = j * p.S + min(s + i, p.S - 1);
+                w4[i] = expf((row[col] - st_s[col * 4 + 1]) * st_s[col * 4]) * st_s[col * 4 + 2];
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (s + i < p.S && w4[i] > best) { best = w4[i]; bi = s + i; }     // first maximum wins (torch.argmax)
+            }
+            const bool valid = n < p.N;
+            const bool inside = valid && in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n, p.wp);
+            idx_s[j * TOK + wt] = valid ? bi : -1;            // density of the next iteration counts every token
+            w_s[j * TOK + wt] = inside ? best : 0.f;          // masked tokens are zero vectors: they add nothing
+            if (p.trace && valid) p.trace[((size_t)it * p.n_tot + o0 + j) * p.N + n] = bi;
+          }
+        }
+        workers_sync();                                       // sims_s is dead from here: it becomes the accumulator
+        // contributing tokens of each instance in token order, split by the parity of the assigned accumulator row (the two
+        // halves of the worker threads own disjoint rows): even rows fill the list bottom-up, odd rows top-down
+        if (warp - 2 < nobj) {
+          const int j = warp - 2;
+          int base0 = 0, base1 = 0;
+          for (int ch = 0; ch < 8; ++ch) {
+            const int t = ch * 32 + lane;
+            if ((ch & 1) == 0 && lane == 0) { ustart_s[j * 5 + (ch >> 1)] = base0; ustart_s[(MAXOBJ + j) * 5 + (ch >> 1)] = base1; }
+            const float wv = w_s[j * TOK + t];
+            const int r = j * p.S + idx_s[j * TOK + t];
+            const bool f0 = wv != 0.f && !(r & 1), f1 = wv != 0.f && (r & 1);
+            const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+            const unsigned lt = (1u << lane) - 1u;
+            if (f0 || f1) {
+              const int pos = f0 ? base0 + __popc(m0 & lt) : TOK - 1 - (base1 + __popc(m1 & lt));
+              const int tr = t & 63;
+              list_s[j * TOK + pos] = (uint32_t)((tr << 7) | ((tr & 7) << 4) | (r << 13));     // XOR with the channel offset = sw128
+              lw_s[j * TOK + pos] = wv * (den_s[t] * (1.f / OP_SCALE));                         // f = (hi + lo) * |f| / 2^10
+            }
+            base0 += __popc(m0); base1 += __popc(m1);
+          }
+          if (lane == 0) { ustart_s[j * 5 + 4] = base0; ustart_s[(MAXOBJ + j) * 5 + 4] = base1; }
+        }
+        mark(5);
+        // thread = two adjacent channels x one row parity
+        const int hpar = wt >> 7, cp = wt & 127, k4 = cp >> 5, c = (cp & 31) * 2;
+        const uint32_t coff = (uint32_t)(((c >> 3) << 4) | ((c & 7) << 1));
+        for (int cc = 0; cc < chunks; ++cc) {
+          for (int i = wt; i < LDK * 256; i += 256) acc_s[i] = 0.f;
+          workers_sync();
+          const bool active = (cc * 4 + k4) < kblocks;
+          int cur[MAXOBJ];
+          float2 run[MAXOBJ];
+#pragma unroll
+          for (int j = 0; j < MAXOBJ; ++j) { cur[j] = -1; run[j] = make_float2(0.f, 0.f); }
+          for (int rb = 0; rb < 4; ++rb) {
+            const uint32_t ub = ucount & 1;
+            mbar_wait(&u_full[ub], (ucount >> 1) & 1);
+            const uint8_t* tile = ring + ub * 65536 + k4 * 16384;
+            if (active) {
+#pragma unroll
+              for (int j = 0; j < MAXOBJ; ++j) {
+                if (j >= nobj) break;
+                const int s0 = ustart_s[(hpar * MAXOBJ + j) * 5 + rb], s1 = ustart_s[(hpar * MAXOBJ + j) * 5 + rb + 1];
+                for (int k0 = s0; k0 < s1; k0 += 8) {
+                  uint32_t e[8];
+                  float2 f[8];
+                  float w[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int kk = min(k0 + i, s1 - 1);
+                    const int pos = j * TOK + (hpar ? TOK - 1 - kk : kk);
+                    e[i] = list_s[pos];
+                    w[i] = lw_s[pos];
+                    const uint32_t off = (e[i] & 0x1fffu) ^ coff;
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(tile + off));
+                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(tile + 8192 + off));
+                    f[i] = make_float2(fh.x + fl.x, fh.y + fl.y);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (k0 + i >= s1) break;
+                    const int r = (int)(e[i] >> 13);
+                    if (r != cur[j]) {
+                      if (cur[j] >= 0) {
+                        float2* a = reinterpret_cast<float2*>(acc_s + cur[j] * 256 + 2 * cp);
+                        a->x += run[j].x; a->y += run[j].y;
+                      }
+                      cur[j] = r; run[j] = make_float2(0.f, 0.f);
+                    }
+                    run[j].x = fmaf(w[i], f[i].x, run[j].x);
+                    run[j].y = fmaf(w[i], f[i].y, run[j].y);
+                  }
+                }
+              }
+            }
+            workers_sync();
+            if (wt == 0) mbar_arrive(&u_empty[ub]);
+            ++ucount;
+          }
+#pragma unroll
+          for (int j = 0; j < MAXOBJ; ++j)
+            if (cur[j] >= 0) {
+              float2* a = reinterpret_cast<float2*>(acc_s + cur[j] * 256 + 2 * cp);
+              a->x += run[j].x; a->y += run[j].y;
+            }
+          workers_sync();
+          // partial prototypes of this 256-channel chunk
+          const int cw = min(256, p.C - cc * 256);
+          if (wt < cw)
+            for (int r = 0; r < kb_cols; ++r)
+              p.proto_part[(((size_t)img * p.G + q) * LDK + r) * p.C + cc * 256 + wt] = acc_s[r * 256 + wt];
+          workers_sync();
+        }
+      }
+      mark(6);
+      bar_target += p.G;
+      group_barrier(ctr, bar_target);
+      mark(7);
+      // ================================================================ phase C: new prototypes
+      phase_c(true);
+      mark(8);
+      bar_target += p.G;
+      group_barrier(ctr, bar_target);
+      mark(9);
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem);
+}
+
+}  // namespace
+
+// den / split tokens are produced by the same kernels as the tc variant
+extern "C" size_t as_mean_shift_fused_workspace(int n_img, int N, int C) {
+  const int G = (N + TOK - 1) / TOK;
+  size_t b = 0;
+  auto add = [&](size_t x) { b += (x + 255) & ~(size_t)255; };
+  add((size_t)n_img * N * C * 2); add((size_t)n_img * N * C * 2);      // hi, lo
+  add((size_t)n_img * N * 4);                                          // den
+  add((size_t)n_img * LDK * C * 2); add((size_t)n_img * LDK * C * 2);  // phat hi, lo
+  add((size_t)n_img * G * LDK * 4); add((size_t)n_img * G * LDK * 8); add((size_t)n_img * G * LDK * 4);
+  add((size_t)n_img * G * LDK * C * 4);                                // proto partials
+  add((size_t)n_img * 4);                                              // barrier counters
+  return b;
+}
+
+static unsigned long long* g_fused_dbg = nullptr;
+// profiling aid: device buffer of [grid][16] uint64 that receives the accumulated nanoseconds per phase (null = off)
+extern "C" void as_mean_shift_fused_debug(unsigned long long* buf) { g_fused_dbg = buf; }
+
+namespace {
+__global__ void fused_split_tokens(const float* __restrict__ feats, long long fstride, int N, int C, __half* __restrict__ hi,
+                                   __half* __restrict__ lo, float* __restrict__ den) {
+  const int img = blockIdx.y;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float* f = feats + img * fstride + (long long)n * C;
+  float ss = 0.f;
+  for (int c = lane_id(); c < C; c += 32) ss += f[c] * f[c];
+  const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
+  if (lane_id() == 0) den[(size_t)img * N + n] = nrm;
+  const size_t o = ((size_t)img * N + n) * C;
+  for (int c = lane_id(); c < C; c += 32) {
+    const float v = f[c] / nrm * OP_SCALE;
+    const __half h = __float2half_rn(v);
+    hi[o + c] = h;
+    lo[o + c] = __float2half_rn(v - __half2float(h));
+  }
+}
+}  // namespace
+
+// Same contract as as_mean_shift_tc; requires C % 64 == 0, C <= 1024, kmax <= 64 and ceil(N/256) <= #SMs.
+extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
+                                   const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois,
+                                   int n_tot, int S, float* proto, float* sim_out, int n_shift, double tau0, double temp,
+                                   int clamp0, int* trace, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  (void)obj_img;
+  if (n_tot <= 0) return 0;
+  const int G = (N + TOK - 1) / TOK;
+  int dev, num_sms;
+  AS_CUDA(cudaGetDevice(&dev));
+  AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (C % 64 || C > 1024 || hp * wp != N || kmax > LDK || kmax < 1 || G > num_sms || (kmax + S - 1) / S > MAXOBJ) return AS_ERR_BAD_ARG;
+  if (workspace_bytes < as_mean_shift_fused_workspace(n_img, N, C)) return AS_ERR_BAD_ARG;
+  char* base = (char*)workspace;
+  size_t off = 0;
+  auto take = [&](size_t x) { char* r = base + off; off += (x + 255) & ~(size_t)255; return r; };
+  __half* hi = (__half*)take((size_t)n_img * N * C * 2);
+  __half* lo = (__half*)take((size_t)n_img * N * C * 2);
+  FusedParams p{};
+  p.den = (float*)take((size_t)n_img * N * 4);
+  p.phat_hi = (__half*)take((size_t)n_img * LDK * C * 2);
+  p.phat_lo = (__half*)take((size_t)n_img * LDK * C * 2);
+  p.colmax_part = (float*)take((size_t)n_img * G * LDK * 4);
+  p.dens_part = (float*)take((size_t)n_img * G * LDK * 8);
+  p.z_part = (float*)take((size_t)n_img * G * LDK * 4);
+  p.proto_part = (float*)take((size_t)n_img * G * LDK * C * 4);
+  p.bar = (unsigned*)take((size_t)n_img * 4);
+  p.n_img = n_img; p.N = N; p.C = C; p.hp = hp; p.wp = wp; p.S = S; p.G = G; p.n_shift = n_shift; p.clamp0 = clamp0;
+  p.tt0 = (float)(temp * tau0); p.temp = (float)temp;
+  p.dbg = g_fused_dbg;
+  p.img_first = img_first; p.img_nobj = img_nobj; p.rois = rois; p.proto = proto; p.sim_out = sim_out; p.trace = trace; p.n_tot = n_tot;
+
+  AS_CUDA(cudaMemsetAsync(p.bar, 0, (size_t)n_img * 4, stream));
+  AS_CUDA(cudaMemsetAsync(p.phat_hi, 0, (size_t)n_img * LDK * C * 2, stream));      // rows past an image's seed count stay zero
+  AS_CUDA(cudaMemsetAsync(p.phat_lo, 0, (size_t)n_img * LDK * C * 2, stream));
+  fused_split_tokens<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, hi, lo, (float*)p.den);
+
+  CUtensorMap tm[4];
+  uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)n_img};
+  uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)N * C * 2};
+  uint32_t box64[3] = {64, 64, 1};
+  int r = as_encode_tmap(&tm[0], hi, 2, 3, dims, str, box64);
+  if (!r) r = as_encode_tmap(&tm[1], lo, 2, 3, dims, str, box64);
+  uint64_t pdims[3] = {(uint64_t)C, (uint64_t)LDK, (uint64_t)n_img};
+  uint64_t pstr[2] = {(uint64_t)C * 2, (uint64_t)LDK * C * 2};
+  if (!r) r = as_encode_tmap(&tm[2], p.phat_hi, 2, 3, pdims, pstr, box64);
+  if (!r) r = as_encode_tmap(&tm[3], p.phat_lo, 2, 3, pdims, pstr, box64);
+  if (r) return r;
+
+  const size_t smem = 1024 + RING + (size_t)TOK * SIM_LD * 4 + /* w, lw, list */ 3 * MAXOBJ * TOK * 4 + /* idx */ MAXOBJ * TOK + TOK * 4 + 256 * 3 * 4 + LDK * 4 * 4 + 2 * MAXOBJ * 5 * 4 + 512;
+  AS_CUDA(cudaFuncSetAttribute(mean_shift_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int groups = num_sms / G;
+  if (groups > n_img) groups = n_img;
+  const int grid = groups * G;
+  void* args[] = {&tm[0], &tm[1], &tm[2], &tm[3], &p};
+  AS_CUDA(cudaLaunchCooperativeKernel((const void*)mean_shift_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args, smem, stream));
+  AS_LAUNCH_CHECK();
+  return 0;
+}

@@ -32,6 +32,9 @@ SIGNATURES = {
     'as_mean_shift': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_mean_shift_tc_workspace': (_sz, [_i, _i, _i, _i, _i, _i]),
     'as_mean_shift_tc': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    'as_mean_shift_fused_workspace': (_sz, [_i, _i, _i]),
+    'as_mean_shift_fused_debug': (None, [_vp]),
+    'as_mean_shift_fused': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'as_rollout_workspace': (_sz, [_i, _i, _i]),

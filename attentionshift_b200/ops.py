@@ -128,11 +128,22 @@ def ctypes_ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_SMS = {}
+
+
+def _num_sms(dev):
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    if i not in _SMS:
+        _SMS[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SMS[i]
+
+
 def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True, want_trace=False,
-               n_per_img=None, use_tensor_cores=True):
+               n_per_img=None, use_tensor_cores=True, impl=None):
     """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C]; instances grouped by image.
     -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None).
-    C % 64 == 0 takes the tensor-core path (batched split-fp16 affinity GEMM); otherwise the fp32 CUDA-core kernels."""
+    impl: 'fused' (one persistent cooperative kernel; C % 64 == 0, <= 64 seed columns per image), 'tc' (batched split-fp16
+    affinity GEMM + small kernels), 'fp32' (CUDA-core kernels, any C); None picks the first that fits."""
     L = _l.load()
     n_tot, S, C = proto.shape
     n_img, N, _ = feats.shape
@@ -143,12 +154,29 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
     if n_per_img is None:
         n_per_img = torch.bincount(obj_img.long(), minlength=n_img).cpu().tolist()      # host sync: pass n_per_img to avoid it
     kmax = max(n_per_img) * S
-    if use_tensor_cores and C % 64 == 0 and kmax <= 256 and S * C * 4 <= 200 * 1024:
+    if impl is None:
+        if not use_tensor_cores or C % 64 != 0:
+            impl = 'fp32'
+        elif C <= 1024 and kmax <= 64 and max(n_per_img) <= 8 and (N + 255) // 256 <= _num_sms(dev):
+            impl = 'fused'
+        elif kmax <= 256 and S * C * 4 <= 200 * 1024:
+            impl = 'tc'
+        else:
+            impl = 'fp32'
+    if impl in ('fused', 'tc'):
         first = [0]
         for k in n_per_img[:-1]:
             first.append(first[-1] + k)
         d_first = torch.tensor(first, dtype=torch.int32).to(dev, non_blocking=True)
         d_nobj = torch.tensor(list(n_per_img), dtype=torch.int32).to(dev, non_blocking=True)
+        if impl == 'fused':
+            nbytes = L.as_mean_shift_fused_workspace(n_img, N, C)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            _l.check(L.as_mean_shift_fused(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(obj_img),
+                                           _l.ptr(d_first), _l.ptr(d_nobj), kmax, _l.ptr(rois), n_tot, S, _l.ptr(proto),
+                                           _l.ptr(sim), n_shift, float(tau), float(temp), int(clamp0), _l.ptr(trace),
+                                           _l.ptr(ws), nbytes, _l.stream_ptr()), 'as_mean_shift_fused')
+            return proto, sim, trace
         nbytes = L.as_mean_shift_tc_workspace(n_img, n_tot, S, N, C, kmax)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         _l.check(L.as_mean_shift_tc(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(obj_img), _l.ptr(d_first),

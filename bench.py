@@ -240,13 +240,16 @@ def run_ours(args):
             roof = dict(kernel='mhsa_fwd_kernel (tcgen05 flash attention, one launch = one layer x batch)', bound='tensor',
                         achieved=round(ach, 1), peak=pk['tf_sus'], unit='TFLOP/s', frac=round(ach / pk['tf_sus'], 4),
                         traffic=traffic, peak_source=pk['src'] + ' sustained bf16 GEMM', share_of_step=round(att['ms'] / args.steps / ms_dev, 3))
-        msf = fam.get('as_mean_shift_tc') or fam.get('as_mean_shift', {})
+        ms_name = next((k for k in ('as_mean_shift_fused', 'as_mean_shift_tc', 'as_mean_shift') if fam.get(k, {}).get('n')), 'as_mean_shift')
+        msf = fam.get(ms_name, {})
         K = cfg['n_obj'] * cfg['seeds']
         b_alg = ((cfg['iters'] + 1) * N * C * 4 + K * N * 4 + 2 * K * C * 4) * B      # SURVEY 8d B_alg per image x images
         roof2 = None
         if msf.get('n'):
             ach2 = b_alg / (msf['ms'] / msf['n'] * 1e-3) / 1e9
-            roof2 = dict(kernel='as_mean_shift_tc (whole on-device attention-shift loop, all images of the batch, ~50 launches)', bound='hbm', achieved=round(ach2, 1),
+            what = {'as_mean_shift_fused': 'one persistent cooperative kernel + the token split kernel',
+                    'as_mean_shift_tc': '~50 launches', 'as_mean_shift': 'fp32 CUDA-core kernels'}[ms_name]
+            roof2 = dict(kernel='%s (whole on-device attention-shift loop, all images of the batch; %s)' % (ms_name, what), bound='hbm', achieved=round(ach2, 1),
                          peak=pk['hbm'], unit='GB/s', frac=round(ach2 / pk['hbm'], 4), traffic=None, peak_source=pk['src'])
         line = dict(metric='images/sec at 1024^2 bs8 ViT-B attn-shift', value=round(world * B / (ms_dev * 1e-3), 2), unit='images/s',
                     n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=round(ms_dev, 3), higher_is_better=True,

@@ -151,6 +151,19 @@ int as_mean_shift_tc(const float* feats, long long feat_img_stride, int n_img, i
                      int S, float* proto, float* sim, int n_shift, double tau0, double temp, int clamp0, int* trace,
                      void* workspace, size_t workspace_bytes, as_stream_t stream);
 
+/* Same contract again as ONE persistent cooperative kernel (the attention-shift loop iterated on the device with no
+ * launch and no host sync per step): an image's tokens are split over ceil(N/256) co-resident CTAs that synchronise
+ * through a global counter; affinity on tcgen05 from split-fp16 operands, softmax / arg-max / prototype update from
+ * shared memory.  Requires C % 64 == 0, C <= 1024, kmax <= 64, at most 8 instances per image, ceil(N/256) <= #SMs;
+ * returns AS_ERR_BAD_ARG otherwise (callers fall back to as_mean_shift_tc).  Replaces RH:830-854 + RH:882-908. */
+size_t as_mean_shift_fused_workspace(int n_img, int N, int C);
+/* profiling aid: device buffer [grid][16] of uint64 receiving accumulated ns per phase of the next calls; NULL = off */
+void as_mean_shift_fused_debug(unsigned long long* buf);
+int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
+                        const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois,
+                        int n_tot, int S, float* proto, float* sim_out, int n_shift, double tau0, double temp,
+                        int clamp0, int* trace, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
 
 int as_filter_seeds(const float* sim, const float* fg_low, int n_tot, int S, int N, float pos_thr, int* keep,

@@ -32,11 +32,11 @@ def _f64_margin_trace(prot, feats, n_shift, tau=0.1, temp=0.1):
     return out
 
 
-@pytest.mark.parametrize('tc', [False, True])
+@pytest.mark.parametrize('impl', ['fp32', 'tc', 'fused'])
 @pytest.mark.parametrize('hp,c,n_obj,S,n_shift,seed', [(14, 32, 2, 20, 5, 11), (28, 64, 3, 20, 10, 3), (28, 64, 3, 16, 5, 5),
                                                        (20, 48, 5, 4, 2, 7), (20, 64, 5, 4, 2, 7), (64, 768, 3, 16, 5, 1)])
-def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed, tc):
-    if tc and c % 64:
+def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed, impl):
+    if impl != 'fp32' and c % 64:
         pytest.skip('tensor-core path needs C % 64 == 0')
     from attentionshift_b200 import ops
     sc = structured_scene(hp, hp, c, n_obj, seed=seed, noise=0.4)
@@ -57,7 +57,7 @@ def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed, tc):
     sel = O.grid_seed_coords(maps, sc['rois'], 0.35, S)
     assert torch.equal(tok.cpu().long(), sel[..., 0] * hp + sel[..., 1])          # seed indices: bit-exact
     prot, sim, tr = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, n_shift, want_trace=True, n_per_img=[n_obj],
-                                   use_tensor_cores=tc)
+                                   impl=impl)
     torch.cuda.synchronize()
 
     # hard assignments: exact wherever the float64 margin is not at rounding level
@@ -80,3 +80,34 @@ def test_mean_shift_vs_oracle(hp, c, n_obj, S, n_shift, seed, tc):
     # (atol is tied to the tensor's scale: near-zero prototype components carry the summation-order noise of N terms)
     torch.testing.assert_close(prot.cpu().flatten(0, 1), o_prot, rtol=1e-3, atol=1e-4 * o_prot.abs().max().item())
     torch.testing.assert_close(sim.cpu().unflatten(-1, (hp, hp)).flatten(0, 1), o_sim, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('n_img,hp,c,S', [(3, 32, 128, 16), (11, 64, 64, 12), (2, 24, 320, 20)])
+def test_fused_matches_tc_multi_image(n_img, hp, c, S):
+    """The persistent kernel against the multi-launch tensor-core variant on a ragged batch (1-3 instances per image; with
+    11 images of 4096 tokens the 16-CTA groups take more than one round over the 148 SMs)."""
+    from attentionshift_b200 import ops
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(100 + n_img)
+    N = hp * hp
+    n_per_img = [1 + (i % 3) for i in range(n_img)]
+    scenes = [structured_scene(hp, hp, c, n_per_img[i], seed=50 + i, noise=0.4) for i in range(n_img)]
+    feats = torch.stack([s['vit_feat'].permute(1, 2, 0).reshape(N, c) for s in scenes]).contiguous().to(dev)
+    obj_img = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(n_per_img)]).to(dev)
+    rois = torch.cat([s['rois'] for s in scenes]).to(dev)
+    maps = torch.cat([torch.stack([((s['labels'] == 2 * j + 1) | (s['labels'] == 2 * j + 2)).float() for j in range(n)])
+                      for s, n in zip(scenes, n_per_img)]).reshape(-1, N).to(dev)
+    _, proto0 = ops.grid_seeds(maps, feats, obj_img, rois, hp, S)
+    out = {}
+    for impl in ('tc', 'fused'):
+        out[impl] = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, 4, want_trace=True, n_per_img=n_per_img, impl=impl)
+    torch.cuda.synchronize()
+    (p_a, s_a, t_a), (p_b, s_b, t_b) = out['tc'], out['fused']
+    agree = (t_a == t_b).float().mean().item()
+    assert agree > 0.999, agree
+    scale = p_a.abs().max().item()
+    assert (p_a - p_b).abs().max().item() <= 2e-3 * scale
+    assert (s_a - s_b).abs().max().item() <= 2e-3
+    # run-to-run determinism of the ordered reductions
+    again = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, 4, want_trace=True, n_per_img=n_per_img, impl='fused')
+    assert torch.equal(again[0], p_b) and torch.equal(again[1], s_b) and torch.equal(again[2], t_b)
