@@ -87,12 +87,25 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// try_wait that may park the thread for up to ~hint_ns before it reports "not yet": the polling loops of the
+// producer / MMA-issuer warps otherwise eat issue slots of the math warps that share their scheduler
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must become a trapped launch, never a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
     if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
   }
 }

@@ -14,6 +14,7 @@
 //                    the transposed map as a split-fp16 pair = the K-major B operand of the roll-out GEMM).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 using namespace asb;
 
@@ -247,6 +248,318 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
+// ------------------------------------------------------------------ forward, second generation
+// Same tiling and TMEM map as mhsa_fwd_kernel; what changed is the schedule of the softmax warps, which were idle 40 %
+// of the time on the exp2 (MUFU) pipe that bounds this kernel:
+//   * one pass over S per tile in the common case: a 32-column chunk is checked against the running offset right after
+//     its TMEM load (FMNMX on the ALU pipe) and exponentiated immediately, while the next chunk's load is in flight; the
+//     two-pass max / rescale path only runs on the first tile, on a ragged last tile and when some row of the warp
+//     leaves the 2^8 window of the lazy rescaling
+//   * S is released to the MMA warp as soon as its last chunk sits in registers, so Q K^T of the next tile overlaps the
+//     second half of the exponentials instead of following them
+//   * the P buffer is handed back in two halves (a commit after the first four P V MMAs): the softmax warps only wait
+//     for P V of the previous tile after they have already computed half of the new probabilities
+//   * K and V^T have separate rings: a K stage is free again after Q K^T, one tile earlier than V^T
+//   * packed fp32x2 FMA / ADD (FFMA2 / FADD2) halve the issue slots of the logit scaling and the row sums
+//   * POLY pairs of every 16-pair chunk take exp2 on the FMA pipe (ex2_poly) instead of MUFU
+constexpr int FWD2_SMEM = 5 * TILE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  return (uint64_t)__float_as_uint(a) | ((uint64_t)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float lo32f(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi32f(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
+template <int POLY>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = smem + TILE_BYTES;          // 2 stages
+  uint8_t* v_s = smem + 3 * TILE_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_half = bars + 12;
+  uint64_t* pv_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_half, 1);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(q_s, &tm_q, q_full, 0, qt * BQ, bh);
+      auto load_k = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_3d(k_s + st * TILE_BYTES, &tm_k, &k_full[st], 0, j * BKV, bh);
+      };
+      load_k(0);
+      for (int j = 0; j < p.nkv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < p.nkv) load_k(j + 1);
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_3d(v_s + st * TILE_BYTES, &tm_v, &v_full[st], j * BKV, 0, bh);
+        tma_load_3d(v_s + st * TILE_BYTES + TILE_BYTES / 2, &tm_v, &v_full[st], j * BKV + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
+    constexpr uint32_t idesc_o = umma_idesc(0, BQ, HD);
+    mbar_wait(q_full, 0);
+    const uint32_t q_base = smem_u32(q_s);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t k_base = smem_u32(k_s + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + COL_S, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
+        tc_commit(&k_empty[st]);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < p.nkv; ++j) {
+      const int st = j & 1;
+      if (j + 1 < p.nkv) issue_s(j + 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_base = smem_u32(v_s + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          mma_f16_ts(tmem + COL_O, tmem + COL_P + k * 8,
+                     umma_desc_k_sw128(v_base + (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32), idesc_o, (j | k) != 0);
+          if (k == 3) tc_commit(pv_half);         // P columns 0..31 (keys 0..63) are consumed
+        }
+        tc_commit(&v_empty[st]);
+        tc_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int t = qt * BQ + row;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint64_t c2 = pack2(p.scale_log2, p.scale_log2);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < p.nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv0 = j * BKV;
+      const bool tail = kv0 + BKV > p.T;
+      bool slow = (j == 0) || tail;
+      if (!slow) {
+        // ---------------- fast path: one pass, chunk c+1 loading while chunk c is exponentiated
+        const float lim = (m_run + 8.f) / p.scale_log2;     // raw-logit bound of the lazy-rescaling window (scale > 0)
+        const uint64_t nm2 = pack2(-m_run, -m_run);
+        uint64_t acc0 = 0ull, acc1 = 0ull;                  // two packed partial row sums
+        uint32_t va[32], vb[32], pk[32];
+        tmem_ld_32x32(lane_addr + COL_S, va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tc_wait_ld();
+          if (c < 3) tmem_ld_32x32(lane_addr + COL_S + (c + 1) * 32, nxt);
+          float mx = fmaxf(__uint_as_float(cur[0]), __uint_as_float(cur[1]));
+          float mxb = fmaxf(__uint_as_float(cur[2]), __uint_as_float(cur[3]));
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) {
+            mx = fmaxf(mx, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+            mxb = fmaxf(mxb, fmaxf(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
+          }
+          if (__any_sync(0xffffffffu, fmaxf(mx, mxb) > lim)) { slow = true; break; }
+          if (c == 3) {                                     // S is in registers and inside the window: release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x = ffma2((uint64_t)cur[2 * i] | ((uint64_t)cur[2 * i + 1] << 32), c2, nm2);
+            float p0, p1;
+            if (i < POLY) { p0 = ex2_poly(lo32f(x)); p1 = ex2_poly(hi32f(x)); }
+            else { p0 = ex2_approx(lo32f(x)); p1 = ex2_approx(hi32f(x)); }
+            if (i & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[(c & 1) * 16 + i] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          if (c & 1) {
+            mbar_wait(c == 1 ? pv_half : pv_done, (j - 1) & 1);     // that half of the P buffer has been consumed (j > 0 here)
+            tc_fence_after();
+            tmem_st_32x32(lane_addr + COL_P + (c >> 1) * 32, pk);
+          }
+        }
+        if (!slow) {
+          const uint64_t a = fadd2(acc0, acc1);
+          l_run += lo32f(a) + hi32f(a);
+        }
+      }
+      if (slow) {
+        // ---------------- slow path: exact two-pass tile (first tile, ragged tail, offset moves).  S is still intact:
+        // the fast path only releases it after every chunk passed the window test.
+        tc_wait_ld();
+        tc_wait_st();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(lane_addr + COL_S + c * 32, va);
+          tmem_ld_32x32(lane_addr + COL_S + c * 32 + 32, vb);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s0 = __uint_as_float(va[i]), s1 = __uint_as_float(vb[i]);
+            if (tail) {
+              if (kv0 + c * 32 + i >= p.T) s0 = -INFINITY;
+              if (kv0 + c * 32 + 32 + i >= p.T) s1 = -INFINITY;
+            }
+            mx = fmaxf(mx, fmaxf(s0, s1));
+          }
+        }
+        const float tmax = mx * p.scale_log2;
+        const bool need = __any_sync(0xffffffffu, tmax > m_run + 8.f);
+        float alpha = 1.f;
+        if (need) {
+          const float m_new = fmaxf(m_run, tmax);
+          alpha = ex2_approx(m_run - m_new);                  // 0 on the first tile (m_run = -inf)
+          m_run = m_new;
+        }
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);            // P buffer and O accumulator are free again
+        tc_fence_after();
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(lane_addr + COL_S + c * 32, va);
+          tmem_ld_32x32(lane_addr + COL_S + c * 32 + 32, vb);
+          tc_wait_ld();
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * i]), p.scale_log2, -m_run));
+            float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * i + 1]), p.scale_log2, -m_run));
+            float p2 = ex2_approx(fmaf(__uint_as_float(vb[2 * i]), p.scale_log2, -m_run));
+            float p3 = ex2_approx(fmaf(__uint_as_float(vb[2 * i + 1]), p.scale_log2, -m_run));
+            if (tail) {
+              if (kv0 + c * 32 + 2 * i >= p.T) p0 = 0.f;
+              if (kv0 + c * 32 + 2 * i + 1 >= p.T) p1 = 0.f;
+              if (kv0 + c * 32 + 32 + 2 * i >= p.T) p2 = 0.f;
+              if (kv0 + c * 32 + 33 + 2 * i >= p.T) p3 = 0.f;
+            }
+            sum += (p0 + p1) + (p2 + p3);
+            __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h01);
+            pk[16 + i] = *reinterpret_cast<uint32_t*>(&h23);
+          }
+          tmem_st_32x32(lane_addr + COL_P + c * 16, pk);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
+        l_run = l_run * alpha + sum;
+        if (need && j > 0) {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + COL_O + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(lane_addr + COL_O + c * 32, v);
+          }
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (p.nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const bool live = t < p.T;
+    __half* dst = p.o + ((size_t)b * p.T + (live ? t : 0)) * (p.heads * HD) + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(lane_addr + COL_O + c * 32, v);
+      tc_wait_ld();
+      if (live) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half2 hh = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * e]) * inv_l, __uint_as_float(v[8 * i + 2 * e + 1]) * inv_l);
+            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          d4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (live) {
+      p.m[(size_t)bh * p.T + t] = m_run;
+      p.l[(size_t)bh * p.T + t] = l_run;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
 // ------------------------------------------------------------------ head-mean probabilities
 constexpr int HM_THREADS = 576;   // TMA warp, MMA warp, 4 x 4 math warps (each quartet covers 32 of the 128 key columns)
 constexpr int HM_MATH = HM_THREADS - 64;
@@ -411,7 +724,24 @@ int encode_qk(CUtensorMap* tm, const void* base, int BH, int T) {
   return as_encode_tmap(tm, base, 2, 3, dims, str, box);
 }
 
+int g_mhsa_variant = -1;
+int mhsa_variant() {
+  if (g_mhsa_variant < 0) {
+    const char* e = getenv("AS_MHSA_VARIANT");
+    g_mhsa_variant = e ? atoi(e) : 2;
+  }
+  return g_mhsa_variant;
+}
+
 }  // namespace
+
+// Schedule of the attention forward: 1 = first-generation kernel (two passes over S per tile), 2 = single-pass schedule
+// (default), 3 / 4 = single-pass with 1/8 resp. 1/4 of the exponentials on the FMA pipe.  Also: env AS_MHSA_VARIANT.
+extern "C" int as_mhsa_set_variant(int v) {
+  if (v < 1 || v > 4) return AS_ERR_BAD_ARG;
+  g_mhsa_variant = v;
+  return 0;
+}
 
 extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T,
                            int Tpad, int heads, cudaStream_t stream) {
@@ -429,13 +759,22 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
   static bool attr = false;
   if (!attr) {
     AS_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
     attr = true;
   }
   FwdParams p;
   p.T = T; p.heads = heads; p.nkv = (T + BKV - 1) / BKV;
   p.scale_log2 = (float)(0.125 * 1.4426950408889634);   // head_dim^-0.5 (VT:67), head_dim = 64
   p.o = (__half*)o; p.m = m; p.l = l;
-  mhsa_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), FWD_THREADS, FWD_SMEM, stream>>>(tm_q, tm_k, tm_v, p);
+  const dim3 grid((T + BQ - 1) / BQ, heads, B);
+  switch (mhsa_variant()) {
+    case 1: mhsa_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    case 3: mhsa_fwd2_kernel<2><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    case 4: mhsa_fwd2_kernel<4><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    default: mhsa_fwd2_kernel<0><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+  }
   AS_LAUNCH_CHECK();
   return 0;
 }

@@ -47,6 +47,10 @@ int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float* bias, voi
 int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T, int Tpad,
                 int heads, as_stream_t stream);
 
+/* Schedule of as_mhsa_fwd (no reference counterpart; benchmarking aid): 1 = two passes over S per tile, 2 = single-pass
+   schedule (default), 3 / 4 = single pass with 1/8 resp. 1/4 of the exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
+int as_mhsa_set_variant(int variant);
+
 /* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,ceil(T/128)] per-tile row sums (may be NULL).
  * t_hi / t_lo (may be NULL): the TRANSPOSED map as a split-fp16 pair (x * t_scale = hi + lo), [B,ldt,ldt], ldt = T rounded
  * up to 128, fully written (zero padded) -- the K-major B operand of the tensor-core roll-out. */
