@@ -717,6 +717,181 @@ attn_headmean_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
+// ------------------------------------------------------------------ head-mean probabilities, persistent schedule
+// Same arithmetic as attn_headmean_kernel, different schedule.  The first kernel spends more time around its 12-head main
+// loop than in it (one CTA per SM: TMA / statistics prologue and the staged 128 KB epilogue of every tile are exposed).
+// Here one CTA per SM walks a contiguous range of (batch, query tile, key tile) triples:
+//   * the TMA producer and the MMA issuer run ahead across tile borders (4-stage operand ring, FOUR S buffers = all 512
+//     TMEM columns), so the next tile's first heads are already in TMEM when the math warps get there
+//   * every math warp stages its 32 x 32 result in a private shared-memory tile and writes it out itself (row-major fp32
+//     and the transposed split-fp16 pair as 16-byte stores covering whole 64 / 128-byte runs, one row-sum partial per
+//     32-column slice): no block barrier, and the stores drain while the next tile's exponentials are running
+//   * the softmax statistics are reloaded only when the (batch, query tile) changes (every ~33 tiles)
+constexpr int HM2_STAGES = 4;
+constexpr int HM2_NBUF = 4;
+constexpr int HM2_SMEM_TILES = 2 * HM2_STAGES * TILE_BYTES;
+constexpr int HM2_WSTAGE = 32 * 33;                          // floats per math warp: its 32 x 32 result, odd row stride
+constexpr int HM2_SMEM = HM2_SMEM_TILES + 1024 + 256 + HM_MAX_HEADS * BQ * 8 + (HM_MATH / 32) * HM2_WSTAGE * 4;
+
+__global__ void __launch_bounds__(HM_THREADS, 1)
+attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const HmParams p,
+                      const int n_tiles, const int tiles_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HM2_SMEM_TILES);
+  uint64_t* full = bars;                         // HM2_STAGES
+  uint64_t* empty = bars + HM2_STAGES;           // HM2_STAGES
+  uint64_t* s_full = bars + 2 * HM2_STAGES;      // HM2_NBUF
+  uint64_t* s_empty = s_full + HM2_NBUF;         // HM2_NBUF
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + HM2_NBUF);
+  float2* ml_s = reinterpret_cast<float2*>(smem + HM2_SMEM_TILES + 256);
+  float* stage_s = reinterpret_cast<float*>(smem + HM2_SMEM_TILES + 256 + HM_MAX_HEADS * BQ * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
+  const int nt = p.ntile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
+    for (int i = 0; i < HM2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < HM2_NBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], HM_MATH / 32); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t g = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        const int b = tile / (nt * nt), r = tile - b * nt * nt, qt = r / nt, kt = r - qt * nt;
+        for (int h = 0; h < p.heads; ++h, ++g) {
+          const uint32_t st = g % HM2_STAGES;
+          mbar_wait(&empty[st], ((g / HM2_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[st], 2 * TILE_BYTES);
+          tma_load_3d(smem + (2 * st) * TILE_BYTES, &tm_q, &full[st], 0, qt * BQ, b * p.heads + h);
+          tma_load_3d(smem + (2 * st + 1) * TILE_BYTES, &tm_k, &full[st], 0, kt * BKV, b * p.heads + h);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
+    const uint32_t total = (uint32_t)max(tile1 - tile0, 0) * (uint32_t)p.heads;
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t st = g % HM2_STAGES, tb = g % HM2_NBUF;
+      mbar_wait(&full[st], (g / HM2_STAGES) & 1);
+      mbar_wait(&s_empty[tb], ((g / HM2_NBUF) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t q_base = smem_u32(smem + (2 * st) * TILE_BYTES), k_base = smem_u32(smem + (2 * st + 1) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + tb * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32), idesc_s, k != 0);
+        tc_commit(&empty[st]);
+        tc_commit(&s_full[tb]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int cslice = (warp - 2) >> 2;                // which 32-column slice of the tile this warp accumulates
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + cslice * 32;
+    const float inv_h = 1.f / (float)p.heads;
+    uint32_t g = 0;
+    int cur_bq = -1;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      const int b = tile / (nt * nt), r = tile - b * nt * nt, qt = r / nt, kt = r - qt * nt;
+      const int t = qt * BQ + row;
+      if (b * nt + qt != cur_bq) {                     // new query tile: softmax row statistics of all heads -> smem
+        cur_bq = b * nt + qt;
+        asm volatile("bar.sync 1, %0;" ::"n"(HM_MATH) : "memory");     // nobody still reads the previous statistics
+        for (int i = threadIdx.x - 64; i < p.heads * BQ; i += HM_MATH) {
+          const int hh = i / BQ, rr = i - hh * BQ, tt = qt * BQ + rr;
+          float2 v = make_float2(0.f, 0.f);              // rows >= T contribute exactly 0
+          if (tt < p.T) {
+            const size_t si = ((size_t)b * p.heads + hh) * p.T + tt;
+            v = make_float2(p.m[si], 1.f / p.l[si]);
+          }
+          ml_s[i] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(HM_MATH) : "memory");
+      }
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      for (int h = 0; h < p.heads; ++h, ++g) {
+        const uint32_t tb = g % HM2_NBUF;
+        const float2 mlv = ml_s[h * BQ + row];
+        const float mrow = mlv.x, inv_l = mlv.y;
+        mbar_wait(&s_full[tb], (g / HM2_NBUF) & 1);
+        tc_fence_after();
+        uint32_t v0[32];
+        tmem_ld_32x32(lane_addr + tb * 128, v0);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[tb]);       // S_h is in registers: a later head's MMA may overwrite the buffer
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          acc[i] = fmaf(ex2_approx(fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow)), inv_l, acc[i]);
+      }
+      // results: through a per-warp staging tile (no block barrier, the stores drain under the next tile's exponentials)
+      // so that every global store instruction writes whole 64 / 128-byte runs
+      const int c0 = kt * BKV + cslice * 32;
+      float* st = stage_s + (warp - 2) * HM2_WSTAGE;
+      float rs = 0.f;
+      __syncwarp();                                    // the previous tile's read-back is complete
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float v = (c0 + i < p.T) ? acc[i] * inv_h : 0.f;
+        rs += v;
+        st[lane * 33 + i] = v;
+      }
+      if (t < p.T && p.rowsum_part) p.rowsum_part[((size_t)b * p.T + t) * (4 * nt) + kt * 4 + cslice] = rs;
+      __syncwarp();
+      {
+        const int rr = lane >> 3, cc = (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r2 = it * 4 + rr, t2 = qt * BQ + quad * 32 + r2;
+          const float* sp = st + r2 * 33 + cc;
+          const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          if (t2 < p.T) *reinterpret_cast<float4*>(p.out + ((size_t)b * p.T + t2) * p.ld + c0 + cc) = v;
+        }
+      }
+      if (p.t_hi) {
+        // transposed tile for the roll-out GEMM (B operand, K-major): At[n = key][k = query], x = hi + lo in fp16; the
+        // padding (key >= T or query >= T) is written as zeros (the staged values are exactly 0 there)
+        const int cb = lane >> 2, r0 = (lane & 3) * 8;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int col = it * 8 + cb;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = st[(r0 + 2 * e) * 33 + col] * p.t_scale, v1 = st[(r0 + 2 * e + 1) * 33 + col] * p.t_scale;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half2 hi = __halves2half2(h0, h1);
+            const __half2 lo = __floats2half2_rn(v0 - __half2float(h0), v1 - __half2float(h1));
+            hw[e] = *reinterpret_cast<const uint32_t*>(&hi);
+            lw[e] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
+          const size_t o = ((size_t)b * p.ldt + c0 + col) * p.ldt + qt * BQ + quad * 32 + r0;
+          *reinterpret_cast<uint4*>(p.t_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(p.t_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 int encode_qk(CUtensorMap* tm, const void* base, int BH, int T) {
   uint64_t dims[3] = {HD, (uint64_t)T, (uint64_t)BH};
   uint64_t str[2] = {HD * 2, (uint64_t)T * HD * 2};
@@ -779,10 +954,11 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
   return 0;
 }
 
-// out [B,T,ld] fp32 (ld >= T), rowsum_part [B,T,ceil(T/128)] (may be null)
+// out [B,T,ld] fp32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] (may be null).  rowsum_slices selects the
+// schedule: 4 = persistent kernel (one row-sum partial per 32-column slice), 1 = first-generation kernel (one per tile).
 extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
-                                float* rowsum_part, void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads,
-                                cudaStream_t stream) {
+                                float* rowsum_part, int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B,
+                                int T, int heads, cudaStream_t stream) {
   if (ld < T || heads > HM_MAX_HEADS) return AS_ERR_BAD_ARG;
   if (t_hi && (!t_lo || ldt != (T + BKV - 1) / BKV * BKV)) return AS_ERR_BAD_ARG;
   CUtensorMap tm_q, tm_k;
@@ -791,8 +967,13 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
   r = encode_qk(&tm_k, k, B * heads, T);
   if (r) return r;
   static bool attr = false;
+  static int num_sms = 0;
   if (!attr) {
+    int dev;
+    AS_CUDA(cudaGetDevice(&dev));
+    AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     AS_CUDA(cudaFuncSetAttribute(attn_headmean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
     attr = true;
   }
   HmParams p;
@@ -800,7 +981,17 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
   p.m = m; p.l = l; p.out = out; p.rowsum_part = rowsum_part; p.ntile = (T + BKV - 1) / BKV;
   p.t_hi = (__half*)t_hi; p.t_lo = (__half*)t_lo; p.ldt = ldt; p.t_scale = t_scale;
   const int nt = (T + BQ - 1) / BQ;
-  attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
+  if (rowsum_slices == 4) {
+    if (ld % 4 || ld < nt * BKV) return AS_ERR_BAD_ARG;   // float4 row stores, whole 128-column tiles
+    const int n_tiles = nt * nt * B;
+    const int per = (n_tiles + num_sms - 1) / num_sms;
+    const int grid = (n_tiles + per - 1) / per;
+    attn_headmean2_kernel<<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
+  } else if (rowsum_slices == 1) {
+    attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
+  } else {
+    return AS_ERR_BAD_ARG;
+  }
   AS_LAUNCH_CHECK();
   return 0;
 }

@@ -3,6 +3,8 @@
 Every function takes/returns CUDA tensors, launches on the current stream and never
 synchronises.  Shapes follow the reference (RH = stdroi_point_deform_attn_reppoints.py,
 VT = models/vision_transformer.py)."""
+import os
+
 import torch
 
 from . import lib as _l
@@ -82,19 +84,24 @@ def mhsa_fwd(q, k, vt, T):
 T_SCALE = 16384.0     # 2^14: head-mean probabilities (<= 1) as split fp16 without touching the subnormal range
 
 
-def attn_headmean(q, k, m, l, T, want_rowsum=True, want_transposed=True):
+HEADMEAN_SLICES = 1 if os.environ.get('AS_HEADMEAN_VARIANT', '2') == '1' else 4
+
+
+def attn_headmean(q, k, m, l, T, want_rowsum=True, want_transposed=True, slices=None):
     """VTD:236/242 attn.mean(1) recomputed from (q, k, m, l).  -> mean [B,T,T] (view of a row-padded buffer).  The
-    tensor carries what the roll-out slab needs as attributes: ``_as_rowsum_part`` [B,T,ceil(T/128)] and, when
-    ``want_transposed``, ``_as_t16`` = (hi, lo) split-fp16 transposed maps [B,Tpad,Tpad] scaled by T_SCALE."""
+    tensor carries what the roll-out slab needs as attributes: ``_as_rowsum_part`` [B,T,slices*ceil(T/128)] and, when
+    ``want_transposed``, ``_as_t16`` = (hi, lo) split-fp16 transposed maps [B,Tpad,Tpad] scaled by T_SCALE.
+    ``slices`` = 4 (default): persistent kernel; 1: one CTA per tile (env AS_HEADMEAN_VARIANT=1)."""
     L = _l.load()
+    slices = HEADMEAN_SLICES if slices is None else slices
     B, heads = q.shape[0], q.shape[1]
     ld = (T + 127) // 128 * 128
     buf = torch.empty(B, T, ld, device=q.device, dtype=torch.float32)
     nt = (T + 127) // 128
-    part = torch.empty(B, T, nt, device=q.device, dtype=torch.float32) if want_rowsum else None
+    part = torch.empty(B, T, slices * nt, device=q.device, dtype=torch.float32) if want_rowsum else None
     thi = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
     tlo = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
-    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), _l.ptr(thi),
+    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), slices, _l.ptr(thi),
                                 _l.ptr(tlo), ld, T_SCALE, B, T, heads, _l.stream_ptr()), 'as_attn_headmean')
     out = buf[:, :, :T]
     out._as_rowsum_part = part

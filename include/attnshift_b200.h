@@ -51,11 +51,14 @@ int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m,
    schedule (default), 3 / 4 = single pass with 1/8 resp. 1/4 of the exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
 int as_mhsa_set_variant(int variant);
 
-/* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,ceil(T/128)] per-tile row sums (may be NULL).
+/* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] partial row sums in
+ * column order (may be NULL).  rowsum_slices = 4: persistent schedule (needs ld = T rounded up to 128), one partial per
+ * 32-column slice; rowsum_slices = 1: one CTA per tile, one partial per 128-column tile.
  * t_hi / t_lo (may be NULL): the TRANSPOSED map as a split-fp16 pair (x * t_scale = hi + lo), [B,ldt,ldt], ldt = T rounded
  * up to 128, fully written (zero padded) -- the K-major B operand of the tensor-core roll-out. */
 int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld, float* rowsum_part,
-                     void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads, as_stream_t stream);
+                     int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads,
+                     as_stream_t stream);
 
 /* Batched f16 x f16 -> f32 GEMM on tcgen05: out[b] = resid[b] + alpha * x[b] w[b]^T (resid may alias out / be NULL). */
 int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M, int N, int K,

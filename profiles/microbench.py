@@ -46,6 +46,7 @@ res['mhsa_fwd'] = (timeit(lambda: ops.mhsa_fwd(q, k, vt, T)), 4 * T * T * C * B)
 o, m, l = ops.mhsa_fwd(q, k, vt, T)
 res['headmean (+transposed)'] = (timeit(lambda: ops.attn_headmean(q, k, m, l, T)), 2 * T * T * C * B)
 res['headmean (no transposed)'] = (timeit(lambda: ops.attn_headmean(q, k, m, l, T, want_transposed=False)), 2 * T * T * C * B)
+res['headmean v1 (+transposed)'] = (timeit(lambda: ops.attn_headmean(q, k, m, l, T, slices=1)), 2 * T * T * C * B)
 res['layernorm'] = (timeit(lambda: ops.layernorm_f16(xf, g, b768)), 0)
 mm = torch.matmul
 res['torch.matmul f16 qkv-shape (cuBLAS)'] = (timeit(lambda: mm(x768, w_qkv.t())), 2 * M * C * 3 * C)
