@@ -16,6 +16,7 @@ call sequence on one generator (exact stream parity; needs one image per call an
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import lib as _l
@@ -41,7 +42,8 @@ class StreamRng:
 class KeyedRng:
     """One torch CPU generator per (image, stage, instance) key.  Same algorithms as torch.randint / torch.randperm
     (mt19937, ``random() % range``, forward Fisher-Yates) so a reference run seeded with ``seed_for(key)`` right before
-    the corresponding call yields identical indices."""
+    the corresponding call yields identical indices.  The raw mt19937 outputs of many keys come from one call into the
+    C ABI (``as_mt19937_draws``), which is what lets the batched host code draw for every instance at once."""
 
     def __init__(self, base_seed=0):
         self.base = int(base_seed)
@@ -50,25 +52,39 @@ class KeyedRng:
         img, stage, obj = key
         return (self.base * 1000003 + img * 10007 + stage * 101 + obj) & 0x7fffffff
 
-    def _gen(self, key):
-        return torch.Generator().manual_seed(self.seed_for(key))
+    def draws(self, keys, k):
+        """Raw 32-bit generator outputs: uint32 array [len(keys), k] (k <= 624)."""
+        L = _l.load()
+        seeds = np.array([self.seed_for(key) for key in keys], dtype=np.uint32)
+        out = np.empty((len(keys), k), dtype=np.uint32)
+        if len(keys) and k:
+            rc = L.as_mt19937_draws(seeds.ctypes.data_as(ctypes.c_void_p), len(keys), k, out.ctypes.data_as(ctypes.c_void_p))
+            if rc != 0:
+                raise ValueError('as_mt19937_draws: bad argument')
+        return out
 
     def randint(self, key, high, n):
-        return torch.randint(high, (n,), generator=self._gen(key))
+        if n > 624:
+            return torch.randint(high, (n,), generator=torch.Generator().manual_seed(self.seed_for(key)))
+        return torch.from_numpy((self.draws([key], n)[0].astype(np.int64) % int(high)))
+
+    @staticmethod
+    def perm_head(raw, n, k):
+        """First k entries of torch.randperm(n) on the CPU (forward Fisher-Yates, TensorFactories.cpp): they depend only on
+        the first k draws z_i = random() % (n - i).  raw: the generator's raw outputs (>= k of them)."""
+        perm, out = {}, []
+        for i in range(min(k, n)):
+            if i < n - 1:
+                j = i + int(raw[i]) % (n - i)
+                vi, vj = perm.get(i, i), perm.get(j, j)
+                perm[i], perm[j] = vj, vi
+                out.append(vj)
+            else:
+                out.append(perm.get(i, i))
+        return out
 
     def randperm_head(self, key, n, k):
-        if n <= 4096:
-            return torch.randperm(n, generator=self._gen(key))[:k]
-        # the first k outputs of torch's CPU randperm (forward Fisher-Yates, TensorFactories.cpp) depend only on its
-        # first k draws z_i = random() % (n - i), which is exactly what torch.randint(n - i, (1,)) consumes
-        g = self._gen(key)
-        perm, out = {}, []
-        for i in range(min(k, n - 1)):
-            j = i + int(torch.randint(n - i, (1,), generator=g))
-            vi, vj = perm.get(i, i), perm.get(j, j)
-            perm[i], perm[j] = vj, vi
-            out.append(vj)
-        return torch.tensor(out, dtype=torch.int64)
+        return torch.tensor(self.perm_head(self.draws([key], min(k, 624))[0], n, k), dtype=torch.int64)
 
 
 def _fill_index(idx, n):
@@ -85,6 +101,25 @@ def _i32(x, dev):
 
 def _f32(x, dev):
     return torch.as_tensor(x, dtype=torch.float32).to(dev, non_blocking=True)
+
+
+def _upload_i32(arrays, dev):
+    """Several small host integer arrays -> the device in ONE pinned, asynchronous copy.  Returns int32 device views (in
+    order, shaped like the inputs).  Pageable uploads stall the host for a driver round trip each; this path has dozens."""
+    arrays = [np.ascontiguousarray(a, dtype=np.int32) for a in arrays]
+    sizes = [a.size for a in arrays]
+    host = torch.empty(max(sum(sizes), 1), dtype=torch.int32, pin_memory=True)
+    hv = host.numpy()
+    o = 0
+    for a, n in zip(arrays, sizes):
+        hv[o:o + n] = a.reshape(-1)
+        o += n
+    d = host.to(dev, non_blocking=True)
+    out, o = [], 0
+    for a, n in zip(arrays, sizes):
+        out.append(d[o:o + n].view(a.shape))
+        o += n
+    return out
 
 
 def _ws(nbytes, dev):
@@ -111,6 +146,21 @@ class _Pending:
     def get(self):
         self.ev.synchronize()
         return self.host
+
+
+_OBJ_IMG = {}
+
+
+def instance_image_index(n_per_img, dev):
+    """obj_img [n_tot] int32 on the device (instance -> image), cached per batch composition (read-only)."""
+    key = (tuple(n_per_img), str(dev))
+    t = _OBJ_IMG.get(key)
+    if t is None:
+        if len(_OBJ_IMG) > 64:
+            _OBJ_IMG.clear()
+        t = torch.repeat_interleave(torch.arange(len(n_per_img), dtype=torch.int32), torch.tensor(list(n_per_img))).to(dev)
+        _OBJ_IMG[key] = t
+    return t
 
 
 def token_major(vit_feat):
@@ -230,17 +280,21 @@ class _Groups:
             self.first.append(self.first[-1] + k)
         self.S = max(2 * k + 1 for k in self.n)
         self.G = len(self.n)
-        self.d_first = _i32(self.first, dev)
-        self.d_n = _i32(self.n, dev)
+        self.d_first, self.d_n = _upload_i32([self.first, self.n], dev)
         self.d_img = torch.arange(self.G, dtype=torch.int32, device=dev)
+        self.d_row_img = self.d_img.repeat_interleave(self.S)
 
 
-def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=0.1):
-    """Candidate counting for the seed sampling (RH:343-352) + asynchronous copy of the counts to the host.  Issue this as
-    early as the selected CAMs exist: the counts cross PCIe while the GPU runs the connected-components stage."""
-    L = _l.load()
-    dev = cam_low.device
-    H = hp * PATCH
+_PLANS = {}
+
+
+def _seed_plan(n_per_img, dev, thr_pos, thr_neg):
+    """Everything about the seed-sampling items that only depends on the instance counts per image: built (and uploaded)
+    once, reused by every later batch of the same composition.  Read-only afterwards."""
+    key = (tuple(n_per_img), str(dev), float(thr_pos), float(thr_neg))
+    plan = _PLANS.get(key)
+    if plan is not None:
+        return plan
     grp = _Groups(n_per_img, dev)
     # items ordered per image as the reference draws them: bg instances, fg instances, supplement
     kinds, ia, ib, thr, item_img, item_slot = [], [], [], [], [], []
@@ -251,19 +305,35 @@ def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=
         for j in range(n):
             kinds.append(1); ia.append(o0 + j); ib.append(0); thr.append(thr_pos); item_img.append(g); item_slot.append(j)
         kinds.append(2); ia.append(o0); ib.append(o0 + n); thr.append(thr_neg); item_img.append(g); item_slot.append(n)
-    n_items = len(kinds)
-    st = dict(grp=grp, kinds=kinds, ia=ia, ib=ib, thr=thr, item_img=item_img, item_slot=item_slot, n_items=n_items,
-              d_kind=_i32(kinds, dev), d_a=_i32(ia, dev), d_b=_i32(ib, dev), cam_low=cam_low, cam_mm=cam_mm, hp=hp, wp=wp)
+    d_kind, d_a, d_b = _upload_i32([kinds, ia, ib], dev)
+    plan = dict(grp=grp, kinds=kinds, ia=ia, ib=ib, thr=thr, item_img=item_img, item_slot=item_slot, n_items=len(kinds),
+                d_kind=d_kind, d_a=d_a, d_b=d_b, d_thr=_f32(thr, dev), np_kind=np.array(kinds), np_a=np.array(ia),
+                np_row=np.array(item_img) * grp.S + np.array(item_slot),
+                keys=[(g, 0, sl) for g, sl in zip(item_img, item_slot)])
+    if len(_PLANS) > 64:
+        _PLANS.clear()
+    _PLANS[key] = plan
+    return plan
 
-    def count(thr_list):
-        d_thr = _f32(thr_list, dev)
+
+def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=0.1):
+    """Candidate counting for the seed sampling (RH:343-352) + asynchronous copy of the counts to the host.  Issue this as
+    early as the selected CAMs exist: the counts cross PCIe while the GPU runs the connected-components stage."""
+    L = _l.load()
+    dev = cam_low.device
+    H = hp * PATCH
+    st = dict(_seed_plan(n_per_img, dev, thr_pos, thr_neg))
+    st.update(cam_low=cam_low, cam_mm=cam_mm, hp=hp, wp=wp)
+    n_items = st['n_items']
+
+    def count(d_thr):
         rc = torch.empty(n_items, H, device=dev, dtype=torch.int32)
         _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(st['d_kind']), _p(st['d_a']), _p(st['d_b']), _p(d_thr), n_items,
                                     hp, wp, _p(rc), _sp()), 'as_norm_rowcount')
-        return rc, d_thr, _Pending(rc.sum(1))
+        return rc, d_thr, _Pending(rc.sum(1, dtype=torch.int32))
 
     st['count'] = count
-    st['rowcnt'], st['d_thr'], st['pending'] = count(thr)
+    st['rowcnt'], st['d_thr'], st['pending'] = count(st['d_thr'])
     return st
 
 
@@ -284,41 +354,45 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
     d_kind, d_a, d_b = st['d_kind'], st['d_a'], st['d_b']
     P = num_points
     rowcnt, d_thr = st['rowcnt'], st['d_thr']
-    totals = st['pending'].get().tolist()                      # host sync (1) -- normally already satisfied
+    totals = st['pending'].get().numpy().astype(np.int64)      # host sync (1) -- normally already satisfied
+    np_kind, np_a, np_row = st['np_kind'], st['np_a'], st['np_row']
     # bg candidates too few -> the reference doubles the threshold until there are enough (RH:360-364)
-    factor = [1.0] * n_items
-    while any(kinds[i] != 1 and totals[i] < P for i in range(n_items)):
-        for i in range(n_items):
-            if kinds[i] != 1 and totals[i] < P:
-                factor[i] *= 2
-        rowcnt, d_thr, pend = st['count']([t * f for t, f in zip(thr, factor)])
-        totals = pend.get().tolist()
-    sel_item, sel_k, sel_dst = [], [], []
-    pts_host = torch.zeros(grp.G, grp.S, P, 2, dtype=torch.int32)
-    gtp = gt_points.detach().cpu()
-    for i in range(n_items):
-        g, slot, num = item_img[i], item_slot[i], totals[i]
-        key = (g, 0, slot)
-        if kinds[i] == 1 and num < P:                        # RH:354-358: all candidates, then the GT point repeated
-            ks = list(range(num))
-            pts_host[g, slot, num:, 0] = int(gtp[ia[i], 0])
-            pts_host[g, slot, num:, 1] = int(gtp[ia[i], 1])
-        else:
-            step = num // P
-            n_draw = len(range(0, num, step))
-            ks = (rng.randint(key, num, n_draw) % num)[:P].tolist()
-        for j, k in enumerate(ks):
-            sel_item.append(i); sel_k.append(k); sel_dst.append((g * grp.S + slot) * P + j)
-    pts = pts_host.to(dev, non_blocking=True)
-    if sel_item:
-        xy = torch.empty(len(sel_item), 2, device=dev, dtype=torch.int32)
-        d_item, d_k = _i32(sel_item, dev), _i32(sel_k, dev)      # keep alive until enqueued (allocator reuse!)
+    factor = np.ones(n_items)
+    while ((np_kind != 1) & (totals < P)).any():
+        factor[(np_kind != 1) & (totals < P)] *= 2
+        rowcnt, d_thr, pend = st['count'](_f32((np.array(thr) * factor).tolist(), dev))
+        totals = pend.get().numpy().astype(np.int64)
+    short = (np_kind == 1) & (totals < P)                    # RH:354-358: all candidates, then the GT point repeated
+    if hasattr(rng, 'draws'):
+        ks = rng.draws(st['keys'], P).astype(np.int64) % np.maximum(totals, 1)[:, None]       # randint(num)[:P]
+    else:                                                    # a single reference-ordered stream: item by item
+        ks = np.zeros((n_items, P), dtype=np.int64)
+        for i in np.nonzero(~short)[0]:
+            num = int(totals[i])
+            n_draw = len(range(0, num, num // P))
+            ks[i] = (rng.randint(st['keys'][i], num, n_draw) % num)[:P].numpy()
+    slot_j = np.arange(P)[None, :]
+    ks = np.where(short[:, None], slot_j, ks)
+    use = ~short[:, None] | (slot_j < totals[:, None])       # which of the P slots are real candidates
+    pts_host = np.zeros((grp.G * grp.S, P, 2), dtype=np.int32)
+    if short.any():
+        gtp = gt_points.detach().cpu().numpy().astype(np.int32)      # int(float) truncation, as the reference's .long()
+        for i in np.nonzero(short)[0]:
+            pts_host[np_row[i], int(totals[i]):] = gtp[np_a[i]]
+    sel_item = np.broadcast_to(np.arange(n_items)[:, None], (n_items, P))[use]
+    sel_k = ks[use]
+    sel_dst = (np_row[:, None] * P + slot_j)[use]
+    n_sel = int(sel_item.size)
+    pts, d_item, d_k, d_dst = _upload_i32([pts_host, sel_item, sel_k, sel_dst], dev)
+    pts = pts.view(grp.G, grp.S, P, 2)
+    if n_sel:
+        xy = torch.empty(n_sel, 2, device=dev, dtype=torch.int32)
         _l.check(L.as_norm_select(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), hp, wp, _p(rowcnt),
-                                  _p(d_item), _p(d_k), len(sel_item), _p(xy), _sp()), 'as_norm_select')
-        pts.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy
+                                  _p(d_item), _p(d_k), n_sel, _p(xy), _sp()), 'as_norm_select')
+        pts.view(-1, 2)[d_dst.long()] = xy
     # ---- prototypes and refinement loop
     GS = grp.G * grp.S
-    row_img = torch.arange(grp.G, dtype=torch.int32, device=dev).repeat_interleave(grp.S)
+    row_img = grp.d_row_img
     proto = torch.empty(grp.G, grp.S, C, device=dev, dtype=torch.float32)
     _l.check(L.as_seed_proto(_p(feats), feats.stride(0), _p(row_img), _p(pts), GS, P, C, hp, wp, _p(proto), _sp()), 'as_seed_proto')
     cur = cosine_maps(feats, grp.d_img, proto)
@@ -359,7 +433,7 @@ def mask_points_begin(map_fg, map_bg, rois, pos_thr=0.6, neg_thr=0.6, corr_size=
     ws = _ws(nbytes, dev)
     _l.check(L.as_mask_candidates(_p(map_fg), _p(map_bg), _p(rois), n_tot, H, W, float(pos_thr), float(neg_thr), int(corr_size),
                                   _p(pos), _p(rowcnt), _p(ws), nbytes, _sp()), 'as_mask_candidates')
-    return dict(pos=pos, rowcnt=rowcnt, ws=ws, map_bg=map_bg, rois=rois, neg_thr=neg_thr, pending=_Pending(rowcnt.sum(1)),
+    return dict(pos=pos, rowcnt=rowcnt, ws=ws, map_bg=map_bg, rois=rois, neg_thr=neg_thr, pending=_Pending(rowcnt.sum(1, dtype=torch.int32)),
                 pending_rois=_Pending(rois.detach().int()), shape=(n_tot, H, W))
 
 
@@ -370,38 +444,42 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
     st = begun if begun is not None else mask_points_begin(map_fg, map_bg, rois, pos_thr, neg_thr, corr_size)
     n_tot, H, W = st['shape']
     pos, rowcnt, ws = st['pos'], st['rowcnt'], st['ws']
-    totals = st['pending'].get().tolist()                    # host sync (2)
-    rois_i = st['pending_rois'].get()
+    totals = st['pending'].get().numpy().astype(np.int64)    # host sync (2): [n_tot, 2] = (#pos, #neg) candidates
+    keys = [(g, 1, j) for g, n in enumerate(n_per_img) for j in range(n)]
+    raw = rng.draws(keys, min(num_gt, 624)) if hasattr(rng, 'draws') else None
     sel_obj, sel_kind, sel_k, sel_dst = [], [], [], []
-    coords = torch.zeros(n_tot, num_gt, 2, dtype=torch.float32)
-    labels = torch.zeros(n_tot, num_gt, dtype=torch.bool)
-    o = 0
-    for g, n in enumerate(n_per_img):
-        for j in range(n):
-            n_pos, n_neg = totals[o]
-            tot = n_pos + n_neg
-            chosen = rng.randperm_head((g, 1, j), tot, num_gt)
-            if chosen.shape[0] < num_gt:
-                if chosen.shape[0] == 0:                     # RH:452-455 sentinel (-1,-1), then the crop offset is added
-                    coords[o, :, 0] = -1.0 + float(rois_i[o, 0])
-                    coords[o, :, 1] = -1.0 + float(rois_i[o, 1])
-                    o += 1
-                    continue
-                chosen = _fill_index(chosen, num_gt)
-            for t, k in enumerate(chosen.tolist()):
-                is_pos = k < n_pos
-                sel_obj.append(o); sel_kind.append(0 if is_pos else 1); sel_k.append(k if is_pos else k - n_pos)
-                sel_dst.append(o * num_gt + t)
-                labels[o, t] = is_pos
-            o += 1
-    coords = coords.to(dev, non_blocking=True)
-    labels = labels.to(dev, non_blocking=True)
-    if sel_obj:
-        xy = torch.empty(len(sel_obj), 2, device=dev, dtype=torch.int32)
-        d_obj, d_kind, d_k = _i32(sel_obj, dev), _i32(sel_kind, dev), _i32(sel_k, dev)
+    coords = np.zeros((n_tot, num_gt, 2), dtype=np.float32)
+    labels = np.zeros((n_tot, num_gt), dtype=np.bool_)
+    rois_i = None
+    for o, key in enumerate(keys):
+        n_pos, n_neg = int(totals[o, 0]), int(totals[o, 1])
+        tot = n_pos + n_neg
+        if raw is not None and num_gt <= 624:
+            chosen = KeyedRng.perm_head(raw[o], tot, num_gt)
+        else:
+            chosen = rng.randperm_head(key, tot, num_gt).tolist()
+        if len(chosen) < num_gt:
+            if len(chosen) == 0:                             # RH:452-455 sentinel (-1,-1), then the crop offset is added
+                rois_i = st['pending_rois'].get() if rois_i is None else rois_i
+                coords[o, :, 0] = -1.0 + float(rois_i[o, 0])
+                coords[o, :, 1] = -1.0 + float(rois_i[o, 1])
+                continue
+            chosen = _fill_index(torch.tensor(chosen), num_gt).tolist()
+        for t, k in enumerate(chosen):
+            is_pos = k < n_pos
+            sel_obj.append(o); sel_kind.append(0 if is_pos else 1); sel_k.append(k if is_pos else k - n_pos)
+            sel_dst.append(o * num_gt + t)
+            labels[o, t] = is_pos
+    n_sel = len(sel_obj)
+    d_coords, d_labels, d_obj, d_kind, d_k, d_dst = _upload_i32([coords.view(np.int32), labels.astype(np.int32), sel_obj, sel_kind,
+                                                                 sel_k, sel_dst], dev)
+    coords = d_coords.view(torch.float32)                    # bit pattern of the fp32 sentinels travels inside the int32 pack
+    labels = d_labels.bool()
+    if n_sel:
+        xy = torch.empty(n_sel, 2, device=dev, dtype=torch.int32)
         _l.check(L.as_mask_select(_p(pos), _p(map_bg), _p(rois), _p(ws), float(neg_thr), _p(rowcnt), _p(d_obj),
-                                  _p(d_kind), _p(d_k), len(sel_obj), H, W, _p(xy), _sp()), 'as_mask_select')
-        coords.view(-1, 2)[torch.as_tensor(sel_dst, device=dev, dtype=torch.long)] = xy.float()
+                                  _p(d_kind), _p(d_k), n_sel, H, W, _p(xy), _sp()), 'as_mask_select')
+        coords.view(-1, 2)[d_dst.long()] = xy.float()
     return coords, labels
 
 
@@ -442,38 +520,53 @@ def semantic_parts(map_fg, feats, obj_img, rois, hp, wp, pos_thr=0.6, n_shift=10
 
 
 def assemble_parts(parts, n_per_img, gt_labels, hp, wp, num_max_keep=50):
-    """Build the reference's ragged python structures (RH:244-262, RH:2024-2031) per image.  One host sync (3)."""
+    """Build the reference's ragged python structures (RH:244-262, RH:2024-2031) per image.  One host sync (3); the valid
+    part centres of the whole batch are gathered by ONE device index_select each (coordinates, features, labels) and
+    handed out as views."""
     n_merged = parts['pending'][0].get().tolist()            # host sync (3)
-    valid = parts['pending'][1].get().bool()
-    out = []
-    o = 0
+    valid = parts['pending'][1].get().numpy().astype(bool)   # [n_tot, KP]
     dev = parts['centers'].device
+    n_tot, KP = valid.shape
+    flat = np.nonzero(valid.reshape(-1))[0]                  # row-major: instance, then part -- the reference's order
+    owner_glob = flat // KP
+    per_obj = valid.sum(1)
+    G = len(n_per_img)
+    firsts = np.concatenate(([0], np.cumsum(n_per_img))).astype(np.int64)
+    lab_firsts = np.concatenate(([0], np.cumsum([int(l.numel()) for l in gt_labels]))).astype(np.int64)
+    lab_all = torch.cat([l.reshape(-1) for l in gt_labels]) if G else torch.zeros(0, dtype=torch.long)
+    owner_img = np.repeat(np.arange(G), n_per_img)[owner_glob]
+    owner_local = owner_glob - firsts[owner_img]             # index of the owning instance inside its image
+    d_flat, d_lab, d_local = _upload_i32([flat, lab_firsts[owner_img] + owner_local, owner_local], dev)
+    d_flat, d_lab, d_local = d_flat.long(), d_lab.long(), d_local.long()
+    C = parts['cfeat'].shape[-1]
+    coords_all = parts['centers'].reshape(-1, 2).index_select(0, d_flat)
+    feats_all = parts['cfeat'].reshape(-1, C).index_select(0, d_flat)
+    labels_all = lab_all.to(dev).index_select(0, d_lab)       # RH:2269-style gather: the label of the owning instance
+    out = []
+    o = c0 = 0
     for g, n in enumerate(n_per_img):
-        sl = slice(o, o + n)
-        v = valid[sl]
-        vd = v.to(dev)
-        coords = parts['centers'][sl][vd]
-        feats = parts['cfeat'][sl][vd]
-        split = v.sum(1).tolist()
-        owner = torch.arange(n).unsqueeze(1).expand_as(v)[v]
-        labels = gt_labels[g][owner.to(gt_labels[g].device)] if coords.shape[0] else gt_labels[g][:0]
+        split = per_obj[o:o + n].tolist()
+        cnt = int(sum(split))
+        coords, feats, labels = coords_all[c0:c0 + cnt], feats_all[c0:c0 + cnt], labels_all[c0:c0 + cnt]
+        owner = d_local[c0:c0 + cnt]
         sim_fg = [parts['part_maps'][o + j, :n_merged[o + j]].unflatten(-1, (hp, wp)) if n_merged[o + j] else torch.zeros(0, 0)
                   for j in range(n)]
-        if coords.shape[0] == 0:
+        if cnt == 0:
             z2 = torch.zeros(0, 2, device=dev)
             out.append(dict(semantic_centers=[z2, labels], semantic_centers_split=[], sim_fg=sim_fg,
                             semantic_centers_feat_split=[], semantic_centers_feat=[], num_parts=split,
                             semantic_centers_org=(z2.clone(), labels.clone()), corres_gts=torch.zeros(0, dtype=torch.long, device=dev)))
         else:
-            c_org, l_org = coords.clone(), labels.clone()
-            if coords.shape[0] > num_max_keep:
-                pick = torch.randperm(coords.shape[0])[:num_max_keep].to(dev)
+            c_org, l_org = coords, labels
+            if cnt > num_max_keep:
+                pick = torch.randperm(cnt)[:num_max_keep].to(dev)
                 coords, labels = coords[pick], labels[pick]
             out.append(dict(semantic_centers=[coords, labels], semantic_centers_split=list(c_org.split(split, dim=0)),
                             sim_fg=sim_fg, semantic_centers_feat_split=list(feats.split(split, dim=0)),
                             semantic_centers_feat=feats, num_parts=split, semantic_centers_org=(c_org, l_org),
-                            corres_gts=owner.to(dev)))
+                            corres_gts=owner))
         o += n
+        c0 += cnt
     return out
 
 

@@ -78,14 +78,22 @@ class AttnShiftRoIHead(nn.Module):
             wh = imgs_whwh.reshape(B, -1)[:, :2] if imgs_whwh is not None else torch.tensor([[wp * 16., hp * 16.]]).repeat(B, 1)
             pos_inds = self.match_points(point_reg, gt_points, wh)
         n_per_img = [int(p.shape[0]) for p in pos_inds]
-        obj_img = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(n_per_img)]).to(dev)
-        obj_pt = torch.cat([p.to(torch.int32) for p in pos_inds]).to(dev)
-        pts = torch.cat([p.float() for p in gt_points]).to(dev).contiguous()
-        labels = [gt_points_labels[i].to(dev) for i in range(B)]       # RH:2269 labels[i][pos_inds]: one label per matched GT
+        n_tot = sum(n_per_img)
+        obj_img = AS.instance_image_index(n_per_img, dev)
+        pts_cat = torch.cat([p.reshape(-1, 2).float() for p in gt_points])
+        pos_cat = torch.cat([p.reshape(-1) for p in pos_inds])
+        if pts_cat.is_cuda or pos_cat.is_cuda:
+            pts, obj_pt = pts_cat.to(dev).contiguous(), pos_cat.to(dev).to(torch.int32)
+        else:
+            # host inputs: ONE pinned upload carries the matched point-token index and the GT point (fp32 bit pattern)
+            obj_pt, pts_bits = AS._upload_i32([pos_cat.numpy(), pts_cat.contiguous().numpy().view('int32')], dev)
+            pts = pts_bits.view(torch.float32)
+        lab_sizes = [int(l.numel()) for l in gt_points_labels[:B]]
+        labels = list(torch.cat([l.reshape(-1) for l in gt_points_labels[:B]]).to(dev, non_blocking=True).split(lab_sizes))
+        # ^ RH:2269 labels[i][pos_inds]: one label per matched GT
         # A5-A7
         rows = AS.rollout_rows(list(attns[-self.cam_layer:]), n_prop)
         cams, mm = AS.cam_maps(rows, obj_img, obj_pt, hp, wp)
-        n_tot = obj_img.shape[0]
         ar = torch.arange(n_tot, device=dev)
         if gt_index is not None:
             gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index

@@ -24,6 +24,7 @@ SIGNATURES = {
     'as_assemble_tokens': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_set_variant': (_i, [_i]),
+    'as_mt19937_draws': (_i, [_vp, _i, _i, _vp]),
     'as_attn_headmean': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
     'as_bgemm_f16_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _f, _vp]),
     'as_rollout_tc_workspace': (_sz, [_i, _i, _i]),

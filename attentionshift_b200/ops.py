@@ -145,6 +145,24 @@ def _num_sms(dev):
     return _SMS[i]
 
 
+_GROUPS = {}
+
+
+def _group_index(n_per_img, dev):
+    """(first instance, instance count) per image as int32 device tensors, cached per batch composition (read-only)."""
+    key = (tuple(n_per_img), str(dev))
+    hit = _GROUPS.get(key)
+    if hit is None:
+        if len(_GROUPS) > 64:
+            _GROUPS.clear()
+        first = [0]
+        for k in list(n_per_img)[:-1]:
+            first.append(first[-1] + k)
+        hit = (torch.tensor(first, dtype=torch.int32).to(dev), torch.tensor(list(n_per_img), dtype=torch.int32).to(dev))
+        _GROUPS[key] = hit
+    return hit
+
+
 def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, clamp0=True, want_trace=False,
                n_per_img=None, use_tensor_cores=True, impl=None):
     """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C]; instances grouped by image.
@@ -171,11 +189,7 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
         else:
             impl = 'fp32'
     if impl in ('fused', 'tc'):
-        first = [0]
-        for k in n_per_img[:-1]:
-            first.append(first[-1] + k)
-        d_first = torch.tensor(first, dtype=torch.int32).to(dev, non_blocking=True)
-        d_nobj = torch.tensor(list(n_per_img), dtype=torch.int32).to(dev, non_blocking=True)
+        d_first, d_nobj = _group_index(n_per_img, dev)
         if impl == 'fused':
             nbytes = L.as_mean_shift_fused_workspace(n_img, N, C)
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)

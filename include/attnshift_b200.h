@@ -181,6 +181,12 @@ int as_part_centers(const float* pmap, const int* n_parts, const float* rois, co
                     long long feat_img_stride, const int* obj_img, int n_tot, int S, int N, int C, int wp, int KP,
                     float* centers, int* valid, int* part_id, float* cfeat, float* stat_scratch, as_stream_t stream);
 
+/* ------------------------------------------------------------------ host-side RNG helper (no device work)
+ * First k (<= 624) raw 32-bit outputs of at::mt19937 seeded like torch.Generator().manual_seed(seed), per key:
+ * out [n_keys][k].  torch.randint(high) = out % high, torch.randperm = forward Fisher-Yates on out[i] % (n - i)
+ * (RH:368, RH:447 draw from torch's CPU generator). */
+int as_mt19937_draws(const unsigned* seeds, int n_keys, int k, unsigned* out);
+
 #ifdef __cplusplus
 }
 #endif
