@@ -5,8 +5,8 @@
 // The up-sampled [7, n_gt, H, W] CAM stack (29 MB per instance at 1024^2) is never written: every consumer
 // re-evaluates the 4-tap interpolation from the [hp, wp] map (16 KB) with the exact arithmetic of
 // torch's CPU kernel:  t = fma(v0, wx0, v1*wx1);  out = fma(t0, wy0, t1*wy1).
-// Connected components: 8-connectivity union-find (label = smallest pixel index of the component); only the
-// partition matters to the caller.  cc_torch itself is absent from the reference tree (parity unpinned, see oracle).
+// Connected components: 8-connectivity union-find over the foreground RUNS of each row (label = smallest run index of
+// the component); only the partition matters to the caller.  cc_torch itself is absent from the reference tree (parity unpinned, see oracle).
 #include "common.cuh"
 #include "upsample.cuh"
 #include <float.h>
@@ -69,7 +69,17 @@ __global__ void minmax_decode(const unsigned* __restrict__ mm, float* __restrict
   if (i < n) out[i] = dec_f(mm[i]);
 }
 
-// ---------------------------------------------------------------- union-find CCL
+// ---------------------------------------------------------------- connected components on run lists
+// The binarised map is a x16 bilinear up-sampling: a row has a handful of foreground runs, so the maps are never
+// labelled pixel by pixel.  Two kernels:
+//   ccl_bitmap  (fully parallel)  fg bit of every pixel -> bitmap [n_maps][H][W/32] (22 MB for 168 maps of 1024^2)
+//   ccl_runs    (one CTA per map) bitmap -> compact run list in row order (block scan over the run-start counts),
+//               8-connectivity union-find over the RUNS (a run meets the runs of the previous row whose columns overlap
+//               [start-1, end+1]: binary search + short walk), areas by one atomic per run, the largest area, the joint
+//               extent of the kept components, and the mirror-expanded box (RH:97-115) -- everything the pixel-based
+//               version spread over five full-resolution passes (~8 GB of traffic per batch).
+// label = smallest run index of the component; only the partition matters to the caller.
+// fg = (v - mn) / clamp(mx - mn, 1e-6) >= thr      (RH:63-66)
 __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   int p = L[x];
   while (p != x) { x = p; p = L[x]; }
@@ -87,163 +97,200 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-// ---- run-based labelling.  A row's maximal foreground runs are the units: every pixel points at its run head, only
-// run heads carry areas / extents, and unions are issued only where a new adjacency can appear (8-connectivity):
-//   up fg            -> union(p, up)       unless left is fg (left already met `up` as its up-right neighbour)
-//   up bg, upleft fg -> union(p, upleft)   unless left is fg (left already met it as its `up`)
-//   up bg, upright fg-> union(p, upright)  always
-// label[p] = head index if foreground else -1;  runlen[head] = run length.
-// fg = (v - mn) / clamp(mx - mn, 1e-6) >= thr      (RH:63-66).   grid (H, n_maps), 256 threads, 4 pixels / thread
+constexpr int BM_ROWS = 8;        // rows per CTA of ccl_bitmap
+// grid (ceil(H / BM_ROWS), n_maps), 256 threads: thread = column (strided), the column's horizontal tap lives in registers
 __global__ void __launch_bounds__(256)
-ccl_init_runs(const float* __restrict__ lows, const float* __restrict__ mmf, int hp, int wp, float thr,
-              int* __restrict__ labels, int* __restrict__ runlen) {
-  __shared__ unsigned bits[128 + 1];              // foreground bitmap of the row (W <= 4096)
-  const int m = blockIdx.y, y = blockIdx.x;
-  const int H = hp * 16, W = wp * 16;
-  const int nw = (W + 31) / 32;
+ccl_bitmap(const float* __restrict__ lows, const float* __restrict__ mmf, int hp, int wp, float thr,
+           unsigned* __restrict__ bits) {
+  extern __shared__ float low_rows[];              // the source rows this CTA touches
+  const int m = blockIdx.y, y0 = blockIdx.x * BM_ROWS;
+  const int H = hp * 16, W = wp * 16, nw = (W + 31) / 32;
   const float* low = lows + (size_t)m * hp * wp;
   const float mn = mmf[2 * m], den = fmaxf(mmf[2 * m + 1] - mn, 1e-6f);
-  int* lab = labels + (size_t)m * H * W + (size_t)y * W;
-  int* rl = runlen + (size_t)m * H * W + (size_t)y * W;
-  const int lane = lane_id();
-  for (int x0 = (threadIdx.x >> 5) * 32; x0 < nw * 32; x0 += blockDim.x) {
-    const int x = x0 + lane;
-    const bool fg = x < W && ((up16(low, hp, wp, y, x) - mn) / den >= thr);
-    const unsigned b = __ballot_sync(0xffffffffu, fg);
-    if (lane == 0) bits[x0 >> 5] = b;
-  }
-  if (threadIdx.x == 0) bits[nw] = 0u;             // sentinel: background past the row end
+  const int y1 = min(y0 + BM_ROWS, H);
+  const int r_lo = tap_up16(y0, hp).i0, r_hi = tap_up16(y1 - 1, hp).i1;
+  const int nr = r_hi - r_lo + 1;
+  for (int i = threadIdx.x; i < nr * wp; i += blockDim.x) low_rows[i] = low[r_lo * wp + i];
   __syncthreads();
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    int w = x >> 5;
-    const int bpos = x & 31;
-    if (!((bits[w] >> bpos) & 1u)) { lab[x] = -1; continue; }
-    // nearest background bit to the left -> run start
-    unsigned inv = ~bits[w] & ((1u << bpos) - 1u);
-    int start;
-    if (inv) {
-      start = (w << 5) + 32 - __clz(inv);
-    } else {
-      int ww = w - 1;
-      while (ww >= 0 && bits[ww] == 0xffffffffu) --ww;
-      start = ww < 0 ? 0 : (ww << 5) + 32 - __clz(~bits[ww]);
+  for (int x0 = (threadIdx.x >> 5) * 32; x0 < nw * 32; x0 += blockDim.x) {
+    const int x = x0 + lane_id();
+    const Tap tx = tap_up16(min(x, W - 1), wp);
+    for (int y = y0; y < y1; ++y) {
+      const Tap ty = tap_up16(y, hp);
+      const float* ra = low_rows + (ty.i0 - r_lo) * wp;
+      const float* rb = low_rows + (ty.i1 - r_lo) * wp;
+      const float v = lerp2(ra[tx.i0], ra[tx.i1], rb[tx.i0], rb[tx.i1], ty, tx);
+      const bool fg = x < W && ((v - mn) / den >= thr);
+      const unsigned b = __ballot_sync(0xffffffffu, fg);
+      if (lane_id() == 0) bits[((size_t)m * H + y) * nw + (x0 >> 5)] = b;
     }
-    lab[x] = (int)((size_t)y * W + start);
-    if (start == x) {                               // run head: nearest background bit to the right -> run end
-      inv = ~bits[w] & ~((bpos == 31) ? 0xffffffffu : ((2u << bpos) - 1u));
+  }
+}
+
+constexpr int CR_THREADS = 1024;
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /* smem [33] */, int* total) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_tot[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_tot[lane] = winc - w;                      // exclusive warp offsets
+    if (lane == 31) warp_tot[32] = winc;
+  }
+  __syncthreads();
+  const int r = warp_tot[warp] + inc - v;
+  *total = warp_tot[32];
+  __syncthreads();
+  return r;
+}
+
+// one CTA per map
+__global__ void __launch_bounds__(CR_THREADS)
+ccl_runs(const unsigned* __restrict__ bits_all, int H, int W, int cap, unsigned short* __restrict__ rs_all,
+         unsigned short* __restrict__ re_all, unsigned short* __restrict__ ry_all, int* __restrict__ label_all,
+         int* __restrict__ area_all, int* __restrict__ rowfirst_all, float ratio, const float* __restrict__ points, int n_tot,
+         float* __restrict__ boxes, unsigned char* __restrict__ keep_mask) {
+  __shared__ int scan_s[33];
+  __shared__ int red_s[5][32];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int nw = (W + 31) / 32;
+  const unsigned* bits = bits_all + (size_t)m * H * nw;
+  unsigned short* rs = rs_all + (size_t)m * cap;
+  unsigned short* re = re_all + (size_t)m * cap;
+  unsigned short* ry = ry_all + (size_t)m * cap;
+  int* label = label_all + (size_t)m * cap;
+  int* area = area_all + (size_t)m * cap;
+  int* row_first = rowfirst_all + (size_t)m * (H + 1);
+
+  // ---- phase 1: run list in (row, column) order
+  int base = 0;
+  const int n_words = H * nw;
+  for (int w0 = 0; w0 < n_words; w0 += CR_THREADS) {
+    const int wi = w0 + tid;
+    unsigned word = 0, starts = 0;
+    int y = 0, wx = 0;
+    if (wi < n_words) {
+      y = wi / nw; wx = wi - y * nw;
+      word = bits[wi];
+      const unsigned prev = wx > 0 ? (bits[wi - 1] >> 31) : 0u;
+      starts = word & ~((word << 1) | prev);
+    }
+    int tot;
+    int off = base + block_excl_scan(__popc(starts), scan_s, &tot);
+    if (wi < n_words && wx == 0) row_first[y] = off;
+    while (starts) {
+      const int b = __ffs(starts) - 1;
+      starts &= starts - 1;
+      // end of the run that starts at bit b of this word: first zero at or after b, possibly in a later word of the row
+      const unsigned inv = ~word & ~((1u << b) - 1u);
       int end;
       if (inv) {
-        end = (w << 5) + __ffs(inv) - 1;
+        end = (wx << 5) + __ffs(inv) - 2;
       } else {
-        int ww = w + 1;
-        while (bits[ww] == 0xffffffffu) ++ww;        // bits[nw] == 0 terminates
-        end = (ww << 5) + __ffs(~bits[ww]) - 1;
+        int ww = wx + 1;
+        unsigned nxt = 0;
+        while (ww < nw && (nxt = bits[(size_t)y * nw + ww]) == 0xffffffffu) ++ww;
+        end = (ww < nw) ? (ww << 5) + __ffs(~nxt) - 2 : nw * 32 - 1;
       }
-      rl[x] = min(end, W) - x;
+      rs[off] = (unsigned short)((wx << 5) + b);
+      re[off] = (unsigned short)min(end, W - 1);
+      ry[off] = (unsigned short)y;
+      label[off] = off;
+      area[off] = 0;
+      ++off;
     }
+    base += tot;
   }
-}
+  const int n_runs = base;
+  if (tid == 0) row_first[H] = n_runs;
+  __syncthreads();
 
-__global__ void ccl_merge_runs(int* __restrict__ labels, int H, int W) {
-  int* lab = labels + (size_t)blockIdx.y * H * W;
-  const int total = H * W;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    if (p < W || lab[p] < 0) continue;
-    const int x = p % W;
-    const bool left = x > 0 && lab[p - 1] >= 0;
-    const bool up = lab[p - W] >= 0;
-    if (up) {
-      if (!left) uf_union(lab, p, p - W);
-    } else {
-      if (!left && x > 0 && lab[p - W - 1] >= 0) uf_union(lab, p, p - W - 1);
-      if (x + 1 < W && lab[p - W + 1] >= 0) uf_union(lab, p, p - W + 1);
+  // ---- phase 2: unions with the overlapping runs of the previous row (8-connectivity: columns [start-1, end+1])
+  for (int i = tid; i < n_runs; i += CR_THREADS) {
+    const int y = ry[i];
+    if (y == 0) continue;
+    const int lo = row_first[y - 1], hi = row_first[y];
+    const int s = (int)rs[i] - 1, e = (int)re[i] + 1;
+    int l = lo, r = hi;                            // first run of the previous row with end >= s
+    while (l < r) {
+      const int mid = (l + r) >> 1;
+      if ((int)re[mid] < s) l = mid + 1; else r = mid;
     }
+    for (int j = l; j < hi && (int)rs[j] <= e; ++j) uf_union(label, i, j);
   }
-}
+  __syncthreads();
 
-// per run head: root, area accumulation (one atomic per run)
-__global__ void ccl_run_area(int* __restrict__ labels, const int* __restrict__ runlen, int* __restrict__ area, int H, int W) {
-  int* lab = labels + (size_t)blockIdx.y * H * W;
-  const int* rl = runlen + (size_t)blockIdx.y * H * W;
-  int* ar = area + (size_t)blockIdx.y * H * W;
-  const int total = H * W;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    const int len = rl[p];
-    if (len <= 0) continue;                 // not a run head
-    const int r = uf_find(lab, p);
-    atomicAdd(&ar[r], len);
-  }
-}
-__global__ void ccl_max_area(const int* __restrict__ area, int H, int W, int* __restrict__ max_area) {
-  const int* ar = area + (size_t)blockIdx.y * H * W;
-  const int total = H * W;
+  // ---- phase 3: areas (one atomic per run), largest area
+  for (int i = tid; i < n_runs; i += CR_THREADS) atomicAdd(&area[uf_find(label, i)], (int)re[i] - (int)rs[i] + 1);
+  __syncthreads();
   int best = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) best = max(best, ar[p]);
+  for (int i = tid; i < n_runs; i += CR_THREADS) best = max(best, area[i]);
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if (lane_id() == 0 && best > 0) atomicMax(max_area + blockIdx.y, best);
-}
-// extent of the kept components from the run heads; ext[m] = {xmin, ymin, xmax, ymax}
-__global__ void ccl_run_extent(int* __restrict__ labels, const int* __restrict__ runlen, const int* __restrict__ area,
-                               const int* __restrict__ max_area, float ratio, int H, int W, int* __restrict__ ext) {
-  const int m = blockIdx.y;
-  int* lab = labels + (size_t)m * H * W;
-  const int* rl = runlen + (size_t)m * H * W;
-  const int* ar = area + (size_t)m * H * W;
-  const float need = ratio * (float)max_area[m];
-  const int total = H * W;
+  if (lane_id() == 0) red_s[0][tid >> 5] = best;
+  __syncthreads();
+  best = red_s[0][lane_id()];
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const float need = ratio * (float)best;
+
+  // ---- phase 4: joint extent of the kept components (area >= ratio * largest, RH:73-83)
   int x0 = INT_MAX, y0 = INT_MAX, x1 = -1, y1 = -1;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    const int len = rl[p];
-    if (len <= 0) continue;
-    const int r = uf_find(lab, p);
-    if ((float)ar[r] >= need) {
-      const int y = p / W, x = p - y * W;
-      x0 = min(x0, x); x1 = max(x1, x + len - 1); y0 = min(y0, y); y1 = max(y1, y);
+  for (int i = tid; i < n_runs; i += CR_THREADS) {
+    if ((float)area[uf_find(label, i)] >= need) {
+      x0 = min(x0, (int)rs[i]); x1 = max(x1, (int)re[i]);
+      y0 = min(y0, (int)ry[i]); y1 = max(y1, (int)ry[i]);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
     x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
     x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
   }
-  if (lane_id() == 0 && x1 >= 0) {
-    atomicMin(ext + 4 * m, x0); atomicMin(ext + 4 * m + 1, y0);
-    atomicMax(ext + 4 * m + 2, x1); atomicMax(ext + 4 * m + 3, y1);
+  if (lane_id() == 0) { red_s[1][tid >> 5] = x0; red_s[2][tid >> 5] = y0; red_s[3][tid >> 5] = x1; red_s[4][tid >> 5] = y1; }
+  __syncthreads();
+  if (tid < 32) {
+    x0 = red_s[1][tid]; y0 = red_s[2][tid]; x1 = red_s[3][tid]; y1 = red_s[4][tid];
+    for (int o = 16; o > 0; o >>= 1) {
+      x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+      x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (tid == 0) {
+      // 'expand' (RH:97-115): mirror the far side of the kept extent around the GT point, clip to the image
+      float* b = boxes + 4 * m;
+      if (x1 < 0) { b[0] = 0.f; b[1] = 0.f; b[2] = 1.f; b[3] = 1.f; }
+      else {
+        const int o = m % n_tot;
+        const float img_w = (float)W, img_h = (float)H;
+        const float px0 = (float)x0, py0 = (float)y0, px1 = (float)x1, py1 = (float)y1;
+        const float xc = points[2 * o], yc = points[2 * o + 1];
+        float bx0, bx1, by0, by1;
+        if (fabsf(xc - px0) > fabsf(xc - px1)) { bx0 = px0; bx1 = xc * 2.f - bx0; bx1 = bx1 < img_w ? bx1 : img_w; }
+        else { bx1 = px1; bx0 = xc * 2.f - bx1; bx0 = bx0 > 0.f ? bx0 : 0.f; }
+        if (fabsf(yc - py0) > fabsf(yc - py1)) { by0 = py0; by1 = yc * 2.f - by0; by1 = by1 < img_h ? by1 : img_h; }
+        else { by1 = py1; by0 = yc * 2.f - by1; by0 = by0 > 0.f ? by0 : 0.f; }
+        b[0] = bx0; b[1] = by0; b[2] = bx1; b[3] = by1;
+      }
+    }
   }
-}
-// optional (tests / visualisation): the reference's remained_label_masks
-__global__ void ccl_keep_mask(int* __restrict__ labels, const int* __restrict__ area, const int* __restrict__ max_area,
-                              float ratio, int H, int W, unsigned char* __restrict__ keep_mask) {
-  const int m = blockIdx.y;
-  int* lab = labels + (size_t)m * H * W;
-  const int* ar = area + (size_t)m * H * W;
-  const float need = ratio * (float)max_area[m];
-  const int total = H * W;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    bool keep = false;
-    if (lab[p] >= 0) keep = (float)ar[uf_find(lab, p)] >= need;
-    keep_mask[(size_t)m * total + p] = keep;
+  // ---- optional (tests / visualisation): the reference's remained_label_masks
+  if (keep_mask) {
+    unsigned char* km = keep_mask + (size_t)m * H * W;
+    for (size_t i = tid; i < (size_t)H * W; i += CR_THREADS) km[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += CR_THREADS)
+      if ((float)area[uf_find(label, i)] >= need)
+        for (int x = rs[i]; x <= (int)re[i]; ++x) km[(size_t)ry[i] * W + x] = 1;
   }
-}
-__global__ void ext_init(int* ext, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ext[i] = (i & 3) < 2 ? INT_MAX : -1;
-}
-// RH:97-115 'expand': mirror the far side of the kept extent around the GT point, clip to the image
-__global__ void cam_expand_box(const int* __restrict__ ext, const float* __restrict__ points /*[n_tot,2] (x,y)*/,
-                               int n_tot, int n_maps, float img_w, float img_h, float* __restrict__ boxes) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_maps) return;
-  const int o = m % n_tot;
-  float* b = boxes + 4 * m;
-  if (ext[4 * m + 2] < 0) { b[0] = 0.f; b[1] = 0.f; b[2] = 1.f; b[3] = 1.f; return; }
-  const float px0 = (float)ext[4 * m], py0 = (float)ext[4 * m + 1], px1 = (float)ext[4 * m + 2], py1 = (float)ext[4 * m + 3];
-  const float xc = points[2 * o], yc = points[2 * o + 1];
-  float x0, x1, y0, y1;
-  if (fabsf(xc - px0) > fabsf(xc - px1)) { x0 = px0; x1 = xc * 2.f - x0; x1 = x1 < img_w ? x1 : img_w; }
-  else { x1 = px1; x0 = xc * 2.f - x1; x0 = x0 > 0.f ? x0 : 0.f; }
-  if (fabsf(yc - py0) > fabsf(yc - py1)) { y0 = py0; y1 = yc * 2.f - y0; y1 = y1 < img_h ? y1 : img_h; }
-  else { y1 = py1; y0 = yc * 2.f - y1; y0 = y0 > 0.f ? y0 : 0.f; }
-  b[0] = x0; b[1] = y0; b[2] = x1; b[3] = y1;
 }
 
 }  // namespace
@@ -272,8 +319,14 @@ extern "C" int as_cam_minmax(const float* lows, int n_maps, int hp, int wp, floa
   return 0;
 }
 
+// run capacity per map: a row of W pixels holds at most ceil(W / 2) runs
+static size_t ccl_cap(int H, int W) { return (size_t)H * ((W + 1) / 2); }
+
 extern "C" size_t as_cam_bbox_workspace(int n_maps, int H, int W) {
-  return (size_t)n_maps * H * W * 12 + (size_t)n_maps * 5 * 4 + 1024;
+  const size_t cap = ccl_cap(H, W);
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  return al((size_t)n_maps * H * ((W + 31) / 32) * 4) + 3 * al((size_t)n_maps * cap * 2) + 2 * al((size_t)n_maps * cap * 4) +
+         al((size_t)n_maps * (H + 1) * 4) + 1024;
 }
 
 // boxes [n_maps,4] for maps ordered [layer][instance] (n_maps = L * n_tot); points [n_tot,2].
@@ -283,22 +336,23 @@ extern "C" int as_cam_bbox(const float* lows, const float* minmax, const float* 
                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (n_maps <= 0) return 0;
   const int H = hp * 16, W = wp * 16;
-  if (W > 4096 || workspace_bytes < as_cam_bbox_workspace(n_maps, H, W)) return AS_ERR_BAD_ARG;
-  int* labels = (int*)workspace;
-  int* area = labels + (size_t)n_maps * H * W;
-  int* runlen = area + (size_t)n_maps * H * W;
-  int* max_area = runlen + (size_t)n_maps * H * W;
-  int* ext = max_area + n_maps;
-  AS_CUDA(cudaMemsetAsync(area, 0, ((size_t)2 * n_maps * H * W + n_maps) * 4, stream));   // area, runlen, max_area
-  ext_init<<<(4 * n_maps + 255) / 256, 256, 0, stream>>>(ext, 4 * n_maps);
-  const dim3 grid(74, n_maps);
-  ccl_init_runs<<<dim3(H, n_maps), 256, 0, stream>>>(lows, minmax, hp, wp, cam_thr, labels, runlen);
-  ccl_merge_runs<<<grid, 256, 0, stream>>>(labels, H, W);
-  ccl_run_area<<<grid, 256, 0, stream>>>(labels, runlen, area, H, W);
-  ccl_max_area<<<grid, 256, 0, stream>>>(area, H, W, max_area);
-  ccl_run_extent<<<grid, 256, 0, stream>>>(labels, runlen, area, max_area, area_ratio, H, W, ext);
-  if (keep_mask) ccl_keep_mask<<<grid, 256, 0, stream>>>(labels, area, max_area, area_ratio, H, W, keep_mask);
-  cam_expand_box<<<(n_maps + 127) / 128, 128, 0, stream>>>(ext, points, n_tot, n_maps, (float)W, (float)H, boxes);
+  if (W > 65535 || H > 65535 || workspace_bytes < as_cam_bbox_workspace(n_maps, H, W)) return AS_ERR_BAD_ARG;
+  const size_t cap = ccl_cap(H, W);
+  const int nw = (W + 31) / 32;
+  char* base = (char*)workspace;
+  size_t off = 0;
+  auto take = [&](size_t x) { char* r = base + off; off += (x + 255) & ~(size_t)255; return r; };
+  unsigned* bits = (unsigned*)take((size_t)n_maps * H * nw * 4);
+  unsigned short* rs = (unsigned short*)take((size_t)n_maps * cap * 2);
+  unsigned short* re = (unsigned short*)take((size_t)n_maps * cap * 2);
+  unsigned short* ry = (unsigned short*)take((size_t)n_maps * cap * 2);
+  int* label = (int*)take((size_t)n_maps * cap * 4);
+  int* area = (int*)take((size_t)n_maps * cap * 4);
+  int* row_first = (int*)take((size_t)n_maps * (H + 1) * 4);
+  const size_t smem = (size_t)(BM_ROWS / 16 + 3) * wp * 4;
+  ccl_bitmap<<<dim3((H + BM_ROWS - 1) / BM_ROWS, n_maps), 256, smem, stream>>>(lows, minmax, hp, wp, cam_thr, bits);
+  ccl_runs<<<n_maps, CR_THREADS, 0, stream>>>(bits, H, W, (int)cap, rs, re, ry, label, area, row_first, area_ratio, points,
+                                              n_tot, boxes, keep_mask);
   AS_LAUNCH_CHECK();
   return 0;
 }
