@@ -73,9 +73,10 @@ __global__ void minmax_decode(const unsigned* __restrict__ mm, float* __restrict
 // The binarised map is a x16 bilinear up-sampling: a row has a handful of foreground runs, so the maps are never
 // labelled pixel by pixel.  Two kernels:
 //   ccl_bitmap  (fully parallel)  fg bit of every pixel -> bitmap [n_maps][H][W/32] (22 MB for 168 maps of 1024^2)
-//   ccl_runs    (one CTA per map) bitmap -> compact run list in row order (block scan over the run-start counts),
-//               8-connectivity union-find over the RUNS (a run meets the runs of the previous row whose columns overlap
-//               [start-1, end+1]: binary search + short walk), areas by one atomic per run, the largest area, the joint
+//   ccl_runs    (one CTA per map) bitmap -> compact run list in row order (thread = row, one block scan),
+//               8-connectivity union-find over the RUNS with the labels in shared memory (a run meets the runs of the
+//               previous row whose columns overlap [start-1, end+1]; their index range is a bitmap rank: prefix count +
+//               popcount), areas by one atomic per distinct root and warp, the largest area, the joint
 //               extent of the kept components, and the mirror-expanded box (RH:97-115) -- everything the pixel-based
 //               version spread over five full-resolution passes (~8 GB of traffic per batch).
 // label = smallest run index of the component; only the partition matters to the caller.
@@ -128,6 +129,8 @@ ccl_bitmap(const float* __restrict__ lows, const float* __restrict__ mmf, int hp
 }
 
 constexpr int CR_THREADS = 1024;
+constexpr int CR_SMEM_RUNS = 24576;              // labels of up to this many runs live in shared memory (96 KB, 2 CTAs / SM)
+
 __device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /* smem [33] */, int* total) {
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   int inc = v;
@@ -156,98 +159,137 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /* smem [33]
   return r;
 }
 
+__device__ __forceinline__ unsigned run_starts(const unsigned* row_bits, int wx) {
+  const unsigned word = row_bits[wx];
+  const unsigned prev = wx > 0 ? (row_bits[wx - 1] >> 31) : 0u;
+  return word & ~((word << 1) | prev);
+}
+
 // one CTA per map
 __global__ void __launch_bounds__(CR_THREADS)
 ccl_runs(const unsigned* __restrict__ bits_all, int H, int W, int cap, unsigned short* __restrict__ rs_all,
          unsigned short* __restrict__ re_all, unsigned short* __restrict__ ry_all, int* __restrict__ label_all,
-         int* __restrict__ area_all, int* __restrict__ rowfirst_all, float ratio, const float* __restrict__ points, int n_tot,
+         int* __restrict__ area_all, int* __restrict__ wordoff_all, float ratio, const float* __restrict__ points, int n_tot,
          float* __restrict__ boxes, unsigned char* __restrict__ keep_mask) {
+  extern __shared__ int label_s[];                 // CR_SMEM_RUNS ints
   __shared__ int scan_s[33];
   __shared__ int red_s[5][32];
-  const int m = blockIdx.x, tid = threadIdx.x;
+  const int m = blockIdx.x, tid = threadIdx.x, lane = lane_id();
   const int nw = (W + 31) / 32;
   const unsigned* bits = bits_all + (size_t)m * H * nw;
   unsigned short* rs = rs_all + (size_t)m * cap;
   unsigned short* re = re_all + (size_t)m * cap;
   unsigned short* ry = ry_all + (size_t)m * cap;
-  int* label = label_all + (size_t)m * cap;
   int* area = area_all + (size_t)m * cap;
-  int* row_first = rowfirst_all + (size_t)m * (H + 1);
+  int* word_off = wordoff_all + (size_t)m * ((size_t)H * nw + 1);   // runs that start before word (y, wx), row-major
 
-  // ---- phase 1: run list in (row, column) order
+  // ---- phase 1: run list in (row, column) order; thread = row (one block scan per 1024 rows)
   int base = 0;
-  const int n_words = H * nw;
-  for (int w0 = 0; w0 < n_words; w0 += CR_THREADS) {
-    const int wi = w0 + tid;
-    unsigned word = 0, starts = 0;
-    int y = 0, wx = 0;
-    if (wi < n_words) {
-      y = wi / nw; wx = wi - y * nw;
-      word = bits[wi];
-      const unsigned prev = wx > 0 ? (bits[wi - 1] >> 31) : 0u;
-      starts = word & ~((word << 1) | prev);
-    }
+  for (int y0 = 0; y0 < H; y0 += CR_THREADS) {
+    const int y = y0 + tid;
+    const unsigned* row = bits + (size_t)y * nw;
+    int cnt = 0;
+    if (y < H)
+      for (int wx = 0; wx < nw; ++wx) cnt += __popc(run_starts(row, wx));
     int tot;
-    int off = base + block_excl_scan(__popc(starts), scan_s, &tot);
-    if (wi < n_words && wx == 0) row_first[y] = off;
-    while (starts) {
-      const int b = __ffs(starts) - 1;
-      starts &= starts - 1;
-      // end of the run that starts at bit b of this word: first zero at or after b, possibly in a later word of the row
-      const unsigned inv = ~word & ~((1u << b) - 1u);
-      int end;
-      if (inv) {
-        end = (wx << 5) + __ffs(inv) - 2;
-      } else {
-        int ww = wx + 1;
-        unsigned nxt = 0;
-        while (ww < nw && (nxt = bits[(size_t)y * nw + ww]) == 0xffffffffu) ++ww;
-        end = (ww < nw) ? (ww << 5) + __ffs(~nxt) - 2 : nw * 32 - 1;
+    int off = base + block_excl_scan(cnt, scan_s, &tot);
+    if (y < H) {
+      for (int wx = 0; wx < nw; ++wx) {
+        word_off[(size_t)y * nw + wx] = off;
+        const unsigned word = row[wx];
+        unsigned starts = run_starts(row, wx);
+        while (starts) {
+          const int b = __ffs(starts) - 1;
+          starts &= starts - 1;
+          // end of the run that starts at bit b: first zero at or after b, possibly in a later word of the row
+          const unsigned inv = ~word & ~((1u << b) - 1u);
+          int end;
+          if (inv) {
+            end = (wx << 5) + __ffs(inv) - 2;
+          } else {
+            int ww = wx + 1;
+            unsigned nxt = 0;
+            while (ww < nw && (nxt = row[ww]) == 0xffffffffu) ++ww;
+            end = (ww < nw) ? (ww << 5) + __ffs(~nxt) - 2 : nw * 32 - 1;
+          }
+          rs[off] = (unsigned short)((wx << 5) + b);
+          re[off] = (unsigned short)min(end, W - 1);
+          ry[off] = (unsigned short)y;
+          ++off;
+        }
       }
-      rs[off] = (unsigned short)((wx << 5) + b);
-      re[off] = (unsigned short)min(end, W - 1);
-      ry[off] = (unsigned short)y;
-      label[off] = off;
-      area[off] = 0;
-      ++off;
     }
     base += tot;
   }
   const int n_runs = base;
-  if (tid == 0) row_first[H] = n_runs;
+  int* label = n_runs <= CR_SMEM_RUNS ? label_s : label_all + (size_t)m * cap;
+  for (int i = tid; i < n_runs; i += CR_THREADS) { label[i] = i; area[i] = 0; }
   __syncthreads();
 
-  // ---- phase 2: unions with the overlapping runs of the previous row (8-connectivity: columns [start-1, end+1])
-  for (int i = tid; i < n_runs; i += CR_THREADS) {
-    const int y = ry[i];
-    if (y == 0) continue;
-    const int lo = row_first[y - 1], hi = row_first[y];
-    const int s = (int)rs[i] - 1, e = (int)re[i] + 1;
-    int l = lo, r = hi;                            // first run of the previous row with end >= s
-    while (l < r) {
-      const int mid = (l + r) >> 1;
-      if ((int)re[mid] < s) l = mid + 1; else r = mid;
+  // ---- phase 2: unions with the overlapping runs of the previous row (8-connectivity: columns [start-1, end+1]).
+  // Their index range follows from the bitmap: rank of a column = runs started up to it = word_off + popcount, all loads
+  // independent.  Runs are visited in row order, 1024 at a time, and compressed after every batch, so the chains a
+  // later find() has to walk stay a couple of links long.
+  for (int i0 = 0; i0 < n_runs; i0 += CR_THREADS) {
+    const int i = i0 + tid;
+    if (i < n_runs) {
+      const int y = ry[i];
+      if (y > 0) {
+        const unsigned* prow = bits + (size_t)(y - 1) * nw;
+        const int* poff = word_off + (size_t)(y - 1) * nw;
+        const int s = (int)rs[i] - 1, e = min((int)re[i] + 1, W - 1);
+        const int we = e >> 5;
+        const int hi = poff[we] + __popc(run_starts(prow, we) & (0xffffffffu >> (31 - (e & 31))));     // starts at columns <= e
+        int lo = poff[0];
+        if (s >= 0) {
+          const int ws = s >> 5;
+          lo = poff[ws] + __popc(run_starts(prow, ws) & (0xffffffffu >> (31 - (s & 31))));               // starts at columns <= s
+          if ((prow[ws] >> (s & 31)) & 1u) --lo;    // the run that covers column s reaches into the window
+        }
+        for (int j = lo; j < hi; ++j) uf_union(label, i, j);
+      }
     }
-    for (int j = l; j < hi && (int)rs[j] <= e; ++j) uf_union(label, i, j);
+    __syncthreads();
+    if (i < n_runs) label[i] = uf_find(label, i);
+    __syncthreads();
+  }
+  // final flattening: label = root
+  for (int i = tid; i < n_runs; i += CR_THREADS) {
+    const int r = uf_find(label, i);
+    label[i] = r;
   }
   __syncthreads();
 
-  // ---- phase 3: areas (one atomic per run), largest area
-  for (int i = tid; i < n_runs; i += CR_THREADS) atomicAdd(&area[uf_find(label, i)], (int)re[i] - (int)rs[i] + 1);
+  // ---- phase 3: areas (runs of a warp mostly share their root: one atomic per distinct root and warp), largest area
+  for (int i0 = 0; i0 < n_runs; i0 += CR_THREADS) {
+    const int i = i0 + tid;
+    const bool on = i < n_runs;
+    const int root = on ? label[i] : -1;
+    const int len = on ? (int)re[i] - (int)rs[i] + 1 : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, on);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int r0 = __shfl_sync(0xffffffffu, root, leader);
+      const bool mine = on && root == r0;
+      const int sum = warp_sum(mine ? len : 0);
+      if (lane == leader) atomicAdd(&area[r0], sum);
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
   __syncthreads();
   int best = 0;
   for (int i = tid; i < n_runs; i += CR_THREADS) best = max(best, area[i]);
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if (lane_id() == 0) red_s[0][tid >> 5] = best;
+  if (lane == 0) red_s[0][tid >> 5] = best;
   __syncthreads();
-  best = red_s[0][lane_id()];
+  best = red_s[0][lane];
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
   const float need = ratio * (float)best;
 
   // ---- phase 4: joint extent of the kept components (area >= ratio * largest, RH:73-83)
   int x0 = INT_MAX, y0 = INT_MAX, x1 = -1, y1 = -1;
   for (int i = tid; i < n_runs; i += CR_THREADS) {
-    if ((float)area[uf_find(label, i)] >= need) {
+    if ((float)area[label[i]] >= need) {
       x0 = min(x0, (int)rs[i]); x1 = max(x1, (int)re[i]);
       y0 = min(y0, (int)ry[i]); y1 = max(y1, (int)ry[i]);
     }
@@ -256,7 +298,7 @@ ccl_runs(const unsigned* __restrict__ bits_all, int H, int W, int cap, unsigned 
     x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
     x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
   }
-  if (lane_id() == 0) { red_s[1][tid >> 5] = x0; red_s[2][tid >> 5] = y0; red_s[3][tid >> 5] = x1; red_s[4][tid >> 5] = y1; }
+  if (lane == 0) { red_s[1][tid >> 5] = x0; red_s[2][tid >> 5] = y0; red_s[3][tid >> 5] = x1; red_s[4][tid >> 5] = y1; }
   __syncthreads();
   if (tid < 32) {
     x0 = red_s[1][tid]; y0 = red_s[2][tid]; x1 = red_s[3][tid]; y1 = red_s[4][tid];
@@ -288,7 +330,7 @@ ccl_runs(const unsigned* __restrict__ bits_all, int H, int W, int cap, unsigned 
     for (size_t i = tid; i < (size_t)H * W; i += CR_THREADS) km[i] = 0;
     __syncthreads();
     for (int i = tid; i < n_runs; i += CR_THREADS)
-      if ((float)area[uf_find(label, i)] >= need)
+      if ((float)area[label[i]] >= need)
         for (int x = rs[i]; x <= (int)re[i]; ++x) km[(size_t)ry[i] * W + x] = 1;
   }
 }
@@ -326,7 +368,7 @@ extern "C" size_t as_cam_bbox_workspace(int n_maps, int H, int W) {
   const size_t cap = ccl_cap(H, W);
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   return al((size_t)n_maps * H * ((W + 31) / 32) * 4) + 3 * al((size_t)n_maps * cap * 2) + 2 * al((size_t)n_maps * cap * 4) +
-         al((size_t)n_maps * (H + 1) * 4) + 1024;
+         al((size_t)n_maps * ((size_t)H * ((W + 31) / 32) + 1) * 4) + 1024;
 }
 
 // boxes [n_maps,4] for maps ordered [layer][instance] (n_maps = L * n_tot); points [n_tot,2].
@@ -348,11 +390,16 @@ extern "C" int as_cam_bbox(const float* lows, const float* minmax, const float* 
   unsigned short* ry = (unsigned short*)take((size_t)n_maps * cap * 2);
   int* label = (int*)take((size_t)n_maps * cap * 4);
   int* area = (int*)take((size_t)n_maps * cap * 4);
-  int* row_first = (int*)take((size_t)n_maps * (H + 1) * 4);
+  int* word_off = (int*)take((size_t)n_maps * ((size_t)H * nw + 1) * 4);
   const size_t smem = (size_t)(BM_ROWS / 16 + 3) * wp * 4;
   ccl_bitmap<<<dim3((H + BM_ROWS - 1) / BM_ROWS, n_maps), 256, smem, stream>>>(lows, minmax, hp, wp, cam_thr, bits);
-  ccl_runs<<<n_maps, CR_THREADS, 0, stream>>>(bits, H, W, (int)cap, rs, re, ry, label, area, row_first, area_ratio, points,
-                                              n_tot, boxes, keep_mask);
+  static bool attr = false;
+  if (!attr) {
+    AS_CUDA(cudaFuncSetAttribute(ccl_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_RUNS * 4));
+    attr = true;
+  }
+  ccl_runs<<<n_maps, CR_THREADS, CR_SMEM_RUNS * 4, stream>>>(bits, H, W, (int)cap, rs, re, ry, label, area, word_off, area_ratio,
+                                                             points, n_tot, boxes, keep_mask);
   AS_LAUNCH_CHECK();
   return 0;
 }
