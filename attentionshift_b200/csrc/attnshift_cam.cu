@@ -98,7 +98,7 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-constexpr int BM_ROWS = 8;        // rows per CTA of ccl_bitmap
+constexpr int BM_ROWS = 32;       // rows per CTA of ccl_bitmap
 // grid (ceil(H / BM_ROWS), n_maps), 256 threads: thread = column (strided), the column's horizontal tap lives in registers
 __global__ void __launch_bounds__(256)
 ccl_bitmap(const float* __restrict__ lows, const float* __restrict__ mmf, int hp, int wp, float thr,
@@ -107,7 +107,7 @@ ccl_bitmap(const float* __restrict__ lows, const float* __restrict__ mmf, int hp
   const int m = blockIdx.y, y0 = blockIdx.x * BM_ROWS;
   const int H = hp * 16, W = wp * 16, nw = (W + 31) / 32;
   const float* low = lows + (size_t)m * hp * wp;
-  const float mn = mmf[2 * m], den = fmaxf(mmf[2 * m + 1] - mn, 1e-6f);
+  const float mn = mmf[2 * m], den = fmaxf(mmf[2 * m + 1] - mn, 1e-6f), rden = __frcp_rn(den);
   const int y1 = min(y0 + BM_ROWS, H);
   const int r_lo = tap_up16(y0, hp).i0, r_hi = tap_up16(y1 - 1, hp).i1;
   const int nr = r_hi - r_lo + 1;
@@ -121,8 +121,11 @@ ccl_bitmap(const float* __restrict__ lows, const float* __restrict__ mmf, int hp
       const float* ra = low_rows + (ty.i0 - r_lo) * wp;
       const float* rb = low_rows + (ty.i1 - r_lo) * wp;
       const float v = lerp2(ra[tx.i0], ra[tx.i1], rb[tx.i0], rb[tx.i1], ty, tx);
-      const bool fg = x < W && ((v - mn) / den >= thr);
-      const unsigned b = __ballot_sync(0xffffffffu, fg);
+      // (v - mn) / den >= thr with the IEEE division only where a reciprocal multiply (<= 2e-7 relative off) cannot decide
+      const float num = v - mn, t = num * rden;
+      bool fg = t >= thr;
+      if (fabsf(t - thr) <= 1e-6f * fmaxf(1.f, fabsf(t))) fg = num / den >= thr;
+      const unsigned b = __ballot_sync(0xffffffffu, fg && x < W);
       if (lane_id() == 0) bits[((size_t)m * H + y) * nw + (x0 >> 5)] = b;
     }
   }

@@ -15,12 +15,14 @@
 //   -- group barrier --
 //   A2 statistics  every CTA combines the partials (fixed order): tau, logit max; partial softmax denominators -> global
 //   -- group barrier --
-//   B  assign      Z; per token and instance the arg-max seed of the softmax weight (first wins) and its weight; one warp
-//                  per instance compacts the contributing (in-box, non-zero weight) tokens into an ordered list
-//      update      token tiles are streamed again (64-row boxes, two 64 KB units in flight, started during assign);
-//                  thread = channel; f is rebuilt as (hi + lo) * |f| / 2^10; listed tokens are fetched 8 at a time;
-//                  run-length accumulation in registers, flushed to a shared-memory accumulator [64 seeds][256 channels]
-//                  only when the assigned seed changes; partials -> global
+//   B  assign      Z; per token and instance the arg-max seed of the softmax weight (first wins) and its weight
+//      update      on the tensor cores as well: D[channel, seed] += F^T[channel, token] . W[seed, token] per 64-token unit
+//                  and 128-channel block.  F^T is the SAME shared-memory token tile the affinity pass uses, addressed as an
+//                  MN-major operand (tokens = K); W is the sparse weight tile (one non-zero per token and instance: weight
+//                  x |f|, scaled by a per-seed power of two and split into fp16 hi + lo) the workers scatter into shared
+//                  memory after the assignment.  hi.hi + hi.lo + lo.hi as in the affinity; the 6 x [128 x 64] fp32
+//                  accumulators stay in TMEM (384 columns) while the token tiles stream through a 4-stage ring; partials
+//                  -> global.  Cost independent of the box sizes (the former gather over listed tokens was not).
 //   -- group barrier --
 //   C  reduce      ordered sum of the G partials -> new prototypes, normalised split-fp16 copy p^ for the next affinity
 //                  (generic stores, fence.proxy.async + the group barrier make them visible to the other CTAs' TMA)
@@ -39,7 +41,11 @@ constexpr int MAXOBJ = 8;
 constexpr int SIM_LD = LDK + 1;
 constexpr int A_STAGE = 32768;           // hi 16 KB + lo 16 KB of a [128 x 64] fp16 tile
 constexpr int B_TILE = 16384;            // hi 8 KB + lo 8 KB of a [64 x 64] seed tile
-constexpr int RING = 3 * A_STAGE + 2 * B_TILE;     // 128 KB: 3 A stages + 2 B tiles (phase A) = 2 units of 64 KB (phase B)
+constexpr int RING = 3 * A_STAGE + 2 * B_TILE;     // 128 KB: 3 A stages + 2 B tiles (phase A) = 4 update stages of 32 KB (phase B)
+constexpr int U_STAGE = 32768;           // [64 tokens x 128 channels] hi + lo: four 8 KB boxes
+constexpr int U_STAGES = RING / U_STAGE;
+constexpr int W_TILE = 16384;            // [64 seeds x 64 tokens] weights, hi 8 KB + lo 8 KB
+constexpr uint32_t TM_UPD = 128;         // first TMEM column of the update accumulators (affinity: 0..127)
 constexpr int FUSED_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 workers
 constexpr float OP_SCALE = 1024.f;
 
@@ -118,17 +124,15 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;                                       // RING bytes
-  float* sims_s = reinterpret_cast<float*>(smem + RING);      // [TOK][SIM_LD]; aliased by the update accumulator [64][256]
-  float* acc_s = sims_s;
+  float* sims_s = reinterpret_cast<float*>(smem + RING);      // [TOK][SIM_LD]
+  uint8_t* wt_s = reinterpret_cast<uint8_t*>(sims_s);         // phase B: 4 weight tiles (one per 64-token unit) alias it
   uint8_t* misc = smem + RING + TOK * SIM_LD * 4;
   float* w_s = reinterpret_cast<float*>(misc);                // [MAXOBJ][TOK] weight of the assigned seed (0 outside the box)
-  float* lw_s = w_s + MAXOBJ * TOK;                           // [MAXOBJ][TOK] listed weights x |f| / 2^10
-  uint32_t* list_s = reinterpret_cast<uint32_t*>(lw_s + MAXOBJ * TOK);     // [MAXOBJ][TOK] listed tokens: tile offset | row << 13
-  float* den_s = reinterpret_cast<float*>(list_s + MAXOBJ * TOK);          // [TOK]
+  float* den_s = w_s + MAXOBJ * TOK;                          // [TOK]
   float* red_s = den_s + TOK;                                 // [256][3]
   float* st_s = red_s + 256 * 3;                              // [LDK][4] 1/tt, column max, 1/Z, tau
-  int* ustart_s = reinterpret_cast<int*>(st_s + LDK * 4);     // [2][MAXOBJ][5] list offsets at the 64-token unit borders
-  int8_t* idx_s = reinterpret_cast<int8_t*>(ustart_s + 2 * MAXOBJ * 5);    // [MAXOBJ][TOK] assigned seed of the previous iteration
+  float* sc_s = st_s + LDK * 4;                               // [LDK][2] weight scale 2^k of the seed, 2^-k / OP_SCALE
+  int8_t* idx_s = reinterpret_cast<int8_t*>(sc_s + LDK * 2);  // [MAXOBJ][TOK] assigned seed of the previous iteration
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + MAXOBJ * TOK);
   bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~(uintptr_t)7);
   uint64_t* a_full = bars;           // 3
@@ -136,29 +140,31 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   uint64_t* b_full = bars + 6;       // 2
   uint64_t* b_empty = bars + 8;      // 2
   uint64_t* acc_full = bars + 10;    // 1
-  uint64_t* u_full = bars + 12;      // 2 (phase B units)
-  uint64_t* u_empty = bars + 14;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* w_full = bars + 11;      // 1 (weight tiles built: 8 worker warps arrive)
+  uint64_t* u_full = bars + 12;      // U_STAGES (phase B token stages)
+  uint64_t* u_empty = bars + 16;     // U_STAGES
+  uint64_t* upd_done = bars + 20;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wt = threadIdx.x - 64;                            // worker thread id 0..255 (negative for warps 0, 1)
   const int groups = gridDim.x / p.G;
   const int grp = blockIdx.x / p.G, q = blockIdx.x % p.G;     // group id, rank inside the group
   const int kblocks = p.C / 64;
-  const int chunks = (p.C + 255) / 256;
+  const int cblocks = p.C / 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_hi64); tma_prefetch_desc(&tm_lo64);
     tma_prefetch_desc(&tm_phi); tma_prefetch_desc(&tm_plo);
     for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
-      mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < U_STAGES; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(w_full, 8);
+    mbar_init(upd_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -168,7 +174,8 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   int a_stage = 0; uint32_t a_phase = 0;        // producer + MMA: A ring
   uint32_t bcount = 0;                          // producer + MMA: B tile uses so far
   uint32_t acount = 0;                          // workers: affinity passes so far
-  uint32_t ucount = 0;                          // producer + workers: phase B units so far
+  uint32_t ucount = 0;                          // producer + MMA: phase B stages so far
+  uint32_t wcount = 0;                          // MMA + workers: update phases so far
 
   uint64_t t_prev = global_timer_ns();
   auto mark = [&](int k) {
@@ -177,7 +184,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   if (grp >= groups) {                          // surplus CTAs (grid not a multiple of G): nothing to do
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<128>(tmem);
+    if (warp == 1) tmem_dealloc<512>(tmem);
     return;
   }
 
@@ -189,10 +196,20 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
     auto tok = [&](int tl) { return ((tl >> 6) * p.G + q) * 64 + (tl & 63); };
     unsigned* ctr = p.bar + img;
     unsigned bar_target = 0;
+    float fmax_cta = 1.f;
     if (wt >= 0) {
       const int n = tok(wt);
-      den_s[wt] = n < p.N ? p.den[(size_t)img * p.N + n] : 1.f;
+      const float dn = n < p.N ? p.den[(size_t)img * p.N + n] : 1.f;
+      den_s[wt] = dn;
       for (int j = 0; j < MAXOBJ; ++j) { idx_s[j * TOK + wt] = -1; w_s[j * TOK + wt] = 0.f; }
+      // largest token norm of this CTA (bounds weight x |f| for the power-of-two scaling of the update's weight tiles)
+      const float wm = warp_max(dn);
+      if (lane == 0) red_s[warp - 2] = wm;
+      workers_sync();
+      float fm = red_s[0];
+      for (int k = 1; k < 8; ++k) fm = fmaxf(fm, red_s[k]);
+      fmax_cta = fm;
+      workers_sync();
     }
     // new prototypes (ordered sum of the group's partials) and their normalised split-fp16 copy, rows q, q+G, ...
     auto phase_c = [&](bool from_partials) {
@@ -449,19 +466,51 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
       // ================================================================ phase B: assign + update
       if (warp == 0) {
         if (lane == 0) {                                      // the ring is free: the update's token tiles start streaming now
-          for (int cc = 0; cc < chunks; ++cc)
-            for (int rb = 0; rb < 4; ++rb) {
-              const uint32_t ub = ucount & 1;
-              mbar_wait(&u_empty[ub], ((ucount >> 1) & 1) ^ 1);
-              const int nk = min(4, kblocks - cc * 4);
-              mbar_expect_tx(&u_full[ub], nk * 16384);
-              for (int k4 = 0; k4 < nk; ++k4) {
-                tma_load_3d(ring + ub * 65536 + k4 * 16384, &tm_hi64, &u_full[ub], (cc * 4 + k4) * 64, (rb * p.G + q) * 64, img);
-                tma_load_3d(ring + ub * 65536 + k4 * 16384 + 8192, &tm_lo64, &u_full[ub], (cc * 4 + k4) * 64, (rb * p.G + q) * 64, img);
-              }
+          // channel blocks in DESCENDING order: the affinity pass before this one finished with the last channels and the
+          // one after it starts with the first, so consecutive passes meet in whatever part of the 100 MB token set the
+          // L2 still holds
+          for (int cb = cblocks - 1; cb >= 0; --cb)
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t st = ucount % U_STAGES;
+              mbar_wait(&u_empty[st], ((ucount / U_STAGES) & 1) ^ 1);
+              mbar_expect_tx(&u_full[st], U_STAGE);
+              uint8_t* dst = ring + st * U_STAGE;
+              const int row0 = (u * p.G + q) * 64;
+              tma_load_3d(dst, &tm_hi64, &u_full[st], (2 * cb) * 64, row0, img);
+              tma_load_3d(dst + 8192, &tm_hi64, &u_full[st], (2 * cb + 1) * 64, row0, img);
+              tma_load_3d(dst + 16384, &tm_lo64, &u_full[st], (2 * cb) * 64, row0, img);
+              tma_load_3d(dst + 24576, &tm_lo64, &u_full[st], (2 * cb + 1) * 64, row0, img);
               ++ucount;
             }
         }
+      } else if (warp == 1) {
+        // D[channel (M = 128: two 64-channel tiles, LBO apart), seed (N = 64)] += F^T . W over the 64 tokens of the unit
+        constexpr uint32_t idesc_u = umma_idesc(0, 128, LDK) | (1u << 15);      // A is MN-major (channels contiguous)
+        mbar_wait(w_full, wcount & 1);
+        tc_fence_after();
+        for (int cb = cblocks - 1; cb >= 0; --cb)
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t st = ucount % U_STAGES;
+            mbar_wait(&u_full[st], (ucount / U_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_hi = smem_u32(ring + st * U_STAGE), a_lo = a_hi + 16384;
+              const uint32_t w_hi = smem_u32(wt_s + u * W_TILE), w_lo = w_hi + 8192;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {                   // 16 tokens per MMA = two 8-token swizzle atoms (SBO = 1024 B)
+                const uint64_t dah = umma_desc_mn_sw128(a_hi + k * 2048, 8192), dal = umma_desc_mn_sw128(a_lo + k * 2048, 8192);
+                const uint64_t dwh = umma_desc_k_sw128(w_hi + k * 32), dwl = umma_desc_k_sw128(w_lo + k * 32);
+                mma_f16_ss(tmem + TM_UPD + cb * LDK, dah, dwh, idesc_u, (u | k) != 0);
+                mma_f16_ss(tmem + TM_UPD + cb * LDK, dah, dwl, idesc_u, 1);
+                mma_f16_ss(tmem + TM_UPD + cb * LDK, dal, dwh, idesc_u, 1);
+              }
+              tc_commit(&u_empty[st]);
+              if (u == 3 && cb == 0) tc_commit(upd_done);
+            }
+            __syncwarp();
+            ++ucount;
+          }
+        ++wcount;
       } else if (wt >= 0) {
         if (wt < kb_cols) st_s[wt * 4 + 2] = 1.f / sum_partials(p.z_part + (size_t)img * p.G * LDK + wt, LDK, p.G);    // fixed order
         workers_sync();
@@ -489,100 +538,53 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
             if (p.trace && valid) p.trace[((size_t)it * p.n_tot + o0 + j) * p.N + n] = bi;
           }
         }
-        workers_sync();                                       // sims_s is dead from here: it becomes the accumulator
-        // contributing tokens of each instance in token order, split by the parity of the assigned accumulator row (the two
-        // halves of the worker threads own disjoint rows): even rows fill the list bottom-up, odd rows top-down
-        if (warp - 2 < nobj) {
-          const int j = warp - 2;
-          int base0 = 0, base1 = 0;
-          for (int ch = 0; ch < 8; ++ch) {
-            const int t = ch * 32 + lane;
-            if ((ch & 1) == 0 && lane == 0) { ustart_s[j * 5 + (ch >> 1)] = base0; ustart_s[(MAXOBJ + j) * 5 + (ch >> 1)] = base1; }
-            const float wv = w_s[j * TOK + t];
-            const int r = j * p.S + idx_s[j * TOK + t];
-            const bool f0 = wv != 0.f && !(r & 1), f1 = wv != 0.f && (r & 1);
-            const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-            const unsigned lt = (1u << lane) - 1u;
-            if (f0 || f1) {
-              const int pos = f0 ? base0 + __popc(m0 & lt) : TOK - 1 - (base1 + __popc(m1 & lt));
-              const int tr = t & 63;
-              list_s[j * TOK + pos] = (uint32_t)((tr << 7) | ((tr & 7) << 4) | (r << 13));     // XOR with the channel offset = sw128
-              lw_s[j * TOK + pos] = wv * (den_s[t] * (1.f / OP_SCALE));                         // f = (hi + lo) * |f| / 2^10
-            }
-            base0 += __popc(m0); base1 += __popc(m1);
-          }
-          if (lane == 0) { ustart_s[j * 5 + 4] = base0; ustart_s[(MAXOBJ + j) * 5 + 4] = base1; }
+        // per-seed power-of-two scale: weight x |f| <= (1/Z) x fmax < 2^10 after scaling, so the fp16 hi + lo split keeps
+        // ~22 bits of the weights that matter
+        if (wt < LDK) {
+          float sc = 1.f;
+          if (wt < kb_cols) sc = exp2f((float)(9 - ilogbf(st_s[wt * 4 + 2] * fmax_cta)));
+          sc_s[wt * 2] = sc;
+          sc_s[wt * 2 + 1] = 1.f / (sc * OP_SCALE);           // f = (hi + lo) * |f| / 2^10: |f| is folded into the weight
         }
-        mark(5);
-        // thread = two adjacent channels x one row parity
-        const int hpar = wt >> 7, cp = wt & 127, k4 = cp >> 5, c = (cp & 31) * 2;
-        const uint32_t coff = (uint32_t)(((c >> 3) << 4) | ((c & 7) << 1));
-        for (int cc = 0; cc < chunks; ++cc) {
-          for (int i = wt; i < LDK * 256; i += 256) acc_s[i] = 0.f;
-          workers_sync();
-          const bool active = (cc * 4 + k4) < kblocks;
-          int cur[MAXOBJ];
-          float2 run[MAXOBJ];
-#pragma unroll
-          for (int j = 0; j < MAXOBJ; ++j) { cur[j] = -1; run[j] = make_float2(0.f, 0.f); }
-          for (int rb = 0; rb < 4; ++rb) {
-            const uint32_t ub = ucount & 1;
-            mbar_wait(&u_full[ub], (ucount >> 1) & 1);
-            const uint8_t* tile = ring + ub * 65536 + k4 * 16384;
-            if (active) {
-#pragma unroll
-              for (int j = 0; j < MAXOBJ; ++j) {
-                if (j >= nobj) break;
-                const int s0 = ustart_s[(hpar * MAXOBJ + j) * 5 + rb], s1 = ustart_s[(hpar * MAXOBJ + j) * 5 + rb + 1];
-                for (int k0 = s0; k0 < s1; k0 += 8) {
-                  uint32_t e[8];
-                  float2 f[8];
-                  float w[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int kk = min(k0 + i, s1 - 1);
-                    const int pos = j * TOK + (hpar ? TOK - 1 - kk : kk);
-                    e[i] = list_s[pos];
-                    w[i] = lw_s[pos];
-                    const uint32_t off = (e[i] & 0x1fffu) ^ coff;
-                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(tile + off));
-                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(tile + 8192 + off));
-                    f[i] = make_float2(fh.x + fl.x, fh.y + fl.y);
-                  }
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    if (k0 + i >= s1) break;
-                    const int r = (int)(e[i] >> 13);
-                    if (r != cur[j]) {
-                      if (cur[j] >= 0) {
-                        float2* a = reinterpret_cast<float2*>(acc_s + cur[j] * 256 + 2 * cp);
-                        a->x += run[j].x; a->y += run[j].y;
-                      }
-                      cur[j] = r; run[j] = make_float2(0.f, 0.f);
-                    }
-                    run[j].x = fmaf(w[i], f[i].x, run[j].x);
-                    run[j].y = fmaf(w[i], f[i].y, run[j].y);
-                  }
-                }
-              }
+        workers_sync();                                       // sims_s is dead from here: it becomes the four weight tiles
+        for (int i = wt; i < 4 * W_TILE / 16; i += 256) reinterpret_cast<uint4*>(wt_s)[i] = make_uint4(0, 0, 0, 0);
+        workers_sync();
+        {
+          const int u = wt >> 6, col = wt & 63;
+          for (int j = 0; j < nobj; ++j) {
+            const float wv = w_s[j * TOK + wt];
+            if (wv != 0.f) {
+              const int r = j * p.S + idx_s[j * TOK + wt];
+              const float v = wv * den_s[wt] * sc_s[r * 2];
+              const __half h = __float2half_rn(v);
+              uint8_t* dst = wt_s + u * W_TILE + sw128(r, col);
+              *reinterpret_cast<__half*>(dst) = h;
+              *reinterpret_cast<__half*>(dst + 8192) = __float2half_rn(v - __half2float(h));
             }
-            workers_sync();
-            if (wt == 0) mbar_arrive(&u_empty[ub]);
-            ++ucount;
           }
+        }
+        fence_proxy_async();                                  // generic-proxy stores -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(w_full);
+        mark(5);
+        // ---- update epilogue: TMEM -> partial prototypes [seed][channel] (lane = channel: coalesced rows)
+        mbar_wait(upd_done, wcount & 1);
+        ++wcount;
+        tc_fence_after();
+        {
+          const int quad = warp & 3, half = (warp - 2) >> 2;
+          for (int cb = half; cb < cblocks; cb += 2) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK, v0);
+            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK + 32, v1);
+            tc_wait_ld();
+            float* dst = p.proto_part + ((size_t)img * p.G + q) * LDK * p.C + cb * 128 + quad * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < MAXOBJ; ++j)
-            if (cur[j] >= 0) {
-              float2* a = reinterpret_cast<float2*>(acc_s + cur[j] * 256 + 2 * cp);
-              a->x += run[j].x; a->y += run[j].y;
-            }
-          workers_sync();
-          // partial prototypes of this 256-channel chunk
-          const int cw = min(256, p.C - cc * 256);
-          if (wt < cw)
-            for (int r = 0; r < kb_cols; ++r)
-              p.proto_part[(((size_t)img * p.G + q) * LDK + r) * p.C + cc * 256 + wt] = acc_s[r * 256 + wt];
-          workers_sync();
+            for (int col = 0; col < LDK; ++col)
+              if (col < kb_cols)
+                dst[(size_t)col * p.C] = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]) * sc_s[col * 2 + 1];
+          }
+          tc_fence_before();
         }
       }
       mark(6);
@@ -600,7 +602,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<128>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace
@@ -644,7 +646,8 @@ __global__ void fused_split_tokens(const float* __restrict__ feats, long long fs
 }
 }  // namespace
 
-// Same contract as as_mean_shift_tc; requires C % 64 == 0, C <= 1024, kmax <= 64 and ceil(N/256) <= #SMs.
+// Same contract as as_mean_shift_tc; requires C % 128 == 0, C <= 768 (the update accumulators of all channels live in TMEM),
+// kmax <= 64 and ceil(N/256) <= #SMs.
 extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
                                    const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois,
                                    int n_tot, int S, float* proto, float* sim_out, int n_shift, double tau0, double temp,
@@ -655,7 +658,7 @@ extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride
   int dev, num_sms;
   AS_CUDA(cudaGetDevice(&dev));
   AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  if (C % 64 || C > 1024 || hp * wp != N || kmax > LDK || kmax < 1 || G > num_sms || (kmax + S - 1) / S > MAXOBJ) return AS_ERR_BAD_ARG;
+  if (C % 128 || C > 768 || hp * wp != N || kmax > LDK || kmax < 1 || G > num_sms || (kmax + S - 1) / S > MAXOBJ) return AS_ERR_BAD_ARG;
   if (workspace_bytes < as_mean_shift_fused_workspace(n_img, N, C)) return AS_ERR_BAD_ARG;
   char* base = (char*)workspace;
   size_t off = 0;
@@ -693,7 +696,8 @@ extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride
   if (!r) r = as_encode_tmap(&tm[3], p.phat_lo, 2, 3, pdims, pstr, box64);
   if (r) return r;
 
-  const size_t smem = 1024 + RING + (size_t)TOK * SIM_LD * 4 + /* w, lw, list */ 3 * MAXOBJ * TOK * 4 + /* idx */ MAXOBJ * TOK + TOK * 4 + 256 * 3 * 4 + LDK * 4 * 4 + 2 * MAXOBJ * 5 * 4 + 512;
+  const size_t smem = 1024 + RING + (size_t)TOK * SIM_LD * 4 + /* w */ MAXOBJ * TOK * 4 + /* idx */ MAXOBJ * TOK + /* den */ TOK * 4 +
+                      /* red */ 256 * 3 * 4 + /* st, sc */ LDK * 6 * 4 + /* barriers */ 256 + 512;
   AS_CUDA(cudaFuncSetAttribute(mean_shift_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int groups = num_sms / G;
   if (groups > n_img) groups = n_img;

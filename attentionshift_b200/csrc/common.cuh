@@ -259,6 +259,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile with the 128-byte swizzle: rows of 128 bytes = 64 consecutive M/N elements of ONE K index, 8 such
+// rows (K indices) per 1024-byte swizzle atom -- i.e. a TMA box {64 elements, rows} read "transposed".  SBO = distance
+// between 8-row groups along K (1024 B when the rows are dense), LBO = distance between 64-element blocks along M/N.
+// The instruction descriptor must flag the operand as MN-major (bit 15 for A, bit 16 for B).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor (upper 32 bits of idesc): c=f32, a/b format (0 f16, 1 bf16, 2 tf32), both K-major
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t m, uint32_t n) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

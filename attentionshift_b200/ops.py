@@ -167,7 +167,7 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
                n_per_img=None, use_tensor_cores=True, impl=None):
     """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C]; instances grouped by image.
     -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None).
-    impl: 'fused' (one persistent cooperative kernel; C % 64 == 0, <= 64 seed columns per image), 'tc' (batched split-fp16
+    impl: 'fused' (one persistent cooperative kernel; C % 128 == 0, C <= 768, <= 64 seed columns per image), 'tc' (batched split-fp16
     affinity GEMM + small kernels), 'fp32' (CUDA-core kernels, any C); None picks the first that fits."""
     L = _l.load()
     n_tot, S, C = proto.shape
@@ -182,7 +182,7 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
     if impl is None:
         if not use_tensor_cores or C % 64 != 0:
             impl = 'fp32'
-        elif C <= 1024 and kmax <= 64 and max(n_per_img) <= 8 and (N + 255) // 256 <= _num_sms(dev):
+        elif C % 128 == 0 and C <= 768 and kmax <= 64 and max(n_per_img) <= 8 and (N + 255) // 256 <= _num_sms(dev):
             impl = 'fused'
         elif kmax <= 256 and S * C * 4 <= 200 * 1024:
             impl = 'tc'

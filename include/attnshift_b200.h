@@ -161,7 +161,7 @@ int as_mean_shift_tc(const float* feats, long long feat_img_stride, int n_img, i
 /* Same contract again as ONE persistent cooperative kernel (the attention-shift loop iterated on the device with no
  * launch and no host sync per step): an image's tokens are split over ceil(N/256) co-resident CTAs that synchronise
  * through a global counter; affinity on tcgen05 from split-fp16 operands, softmax / arg-max / prototype update from
- * shared memory.  Requires C % 64 == 0, C <= 1024, kmax <= 64, at most 8 instances per image, ceil(N/256) <= #SMs;
+ * shared memory.  Requires C % 128 == 0, C <= 768, kmax <= 64, at most 8 instances per image, ceil(N/256) <= #SMs;
  * returns AS_ERR_BAD_ARG otherwise (callers fall back to as_mean_shift_tc).  Replaces RH:830-854 + RH:882-908. */
 size_t as_mean_shift_fused_workspace(int n_img, int N, int C);
 /* profiling aid: device buffer [grid][16] of uint64 receiving accumulated ns per phase of the next calls; NULL = off */

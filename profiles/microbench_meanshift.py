@@ -45,8 +45,8 @@ ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, iters, n_per_img=npi, impl=
 torch.cuda.synchronize()
 L.as_mean_shift_fused_debug(None)
 d = dbg.view(148, 16)[:128].double() / 1e3
-names = ['0 seeds p^ + barrier', '1 affinity epilogue + column stats', '2 barrier 1', '3 statistics / partial Z', '4 barrier 2', '5 assign',
-         '6 update', '7 barrier 3', '8 reduce', '9 barrier 4', '10 affinity main loop (TMA + tcgen05)']
+names = ['0 seeds p^ + barrier', '1 affinity epilogue + column stats', '2 barrier 1', '3 statistics / partial Z', '4 barrier 2', '5 assign + weight tiles',
+         '6 update (tcgen05) + epilogue', '7 barrier 3', '8 reduce', '9 barrier 4', '10 affinity main loop (TMA + tcgen05)']
 print('phase                              mean us   max us   (worker thread 0 of each CTA, summed over the call)')
 for k, nme in enumerate(names):
     print(f'{nme:34s} {d[:, k].mean().item():8.1f} {d[:, k].max().item():8.1f}')
