@@ -18,7 +18,8 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 8 * 4096;   // one 32 x 32 fp32 tile per epilogue warp (XOR-swizzled, no padding)
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 128 columns each)
 
 enum { EPI_F16 = 0, EPI_GELU_F16 = 1, EPI_RESID_F32 = 2, EPI_QKV = 3, EPI_F32 = 4 };
@@ -58,24 +59,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), e, hx);                            // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
 
-__device__ __forceinline__ void store_f16x32(__half* dst, const float* f) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
-    __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
-    __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
-    __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    u.z = *reinterpret_cast<uint32_t*>(&h2);
-    u.w = *reinterpret_cast<uint32_t*>(&h3);
-    d4[i] = u;
-  }
-}
-
-template <int kPair>     // 2: a pair of CTAs (cluster of 2) drives ONE cta_group::2 MMA of shape 256x256; 1: stand-alone CTA, 128x256
+template <int kPair, int kEpi>     // kEpi: epilogue mode, compiled in (keeps the staged epilogue inside the register budget); kPair 2: a pair of CTAs (cluster of 2) drives ONE cta_group::2 MMA of shape 256x256; 1: stand-alone CTA, 128x256
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const GemmParams p) {
@@ -84,12 +68,13 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   // operand reads instead of 192 B/clk -- the single-CTA shape is shared-memory-bandwidth bound near 45% tensor utilisation.
   constexpr int kStages = kPair == 2 ? 6 : 4;
   constexpr int kBBytes = kPair == 2 ? B_BYTES / 2 : B_BYTES;
-  static_assert(kStages * (A_BYTES + kBBytes) + 1024 + 256 <= SMEM_BYTES, "smem budget");
+  static_assert(kStages * (A_BYTES + kBBytes) + EPI_STAGE_BYTES + 1024 + 256 <= SMEM_BYTES, "smem budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * (A_BYTES + kBBytes));
+  uint8_t* epi_s = smem + kStages * (A_BYTES + kBBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_s + EPI_STAGE_BYTES);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
@@ -195,50 +180,60 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       }
     }
   } else {
+    // Thread = accumulator row (that is how tcgen05.ld hands the tile out), but a warp-wide store of 16 bytes per ROW
+    // touches 32 cache lines and costs the LSU 32 cycles -- the K = 768 GEMMs were bound by exactly that.  Every 32 x 32
+    // chunk therefore crosses a private, XOR-swizzled shared-memory tile and leaves (and the residual arrives) with each
+    // instruction covering whole 128-byte (fp32) / 64-byte (fp16) row segments.
     const int quad = warp & 3;  // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;   // which 128-column half of the accumulator this warp drains
+    float* st32 = reinterpret_cast<float*>(epi_s + (warp - 2) * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int C = p.heads * 64;
+    const int r4 = lane >> 3, c4 = lane & 7;        // fp32 read-back: row 4i + r4, float4 column c4
+    const int r8 = lane >> 2, c8 = lane & 3;        // fp16 read-back: row 8i + r8, 16-byte piece c8
     for (int tile = cluster_id; tile < tiles; tile += n_clusters) {
       const int bi = tile / tiles_per_batch, tb = tile - bi * tiles_per_batch;
       const int m_blk = kPair * (tb / num_n) + rank, n_blk = tb % num_n;
-      const int m = m_blk * BM + quad * 32 + lane;
+      const int m0 = m_blk * BM + quad * 32;         // first row of this warp's 32-row slab
+      const int m = m0 + lane;
       const int c_beg = chalf * (BN / 64), c_end = (chalf + 1) * (BN / 64);
       const bool live = m < p.M;
       // the residual does not depend on the MMA: fetch the first chunk before the accumulator is ready and always keep
-      // the next chunk's loads in flight (the K=768 GEMMs were bound by this load latency)
+      // the next chunk's loads in flight
       float4 rnext[8];
-      const float* rrow = nullptr;
-      if (p.epi == EPI_RESID_F32) {
-        rrow = p.resid + bi * p.resid_bstride + (size_t)(live ? m : 0) * p.ldo;
+      const float* rbase = nullptr;
+      if (kEpi == EPI_RESID_F32) {
+        rbase = p.resid + bi * p.resid_bstride;
         const int n0 = n_blk * BN + c_beg * 32;
-        if (live && n0 < p.N) {
+        if (n0 < p.N) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + n0) + i);
+          for (int i = 0; i < 8; ++i) {
+            const int mr = m0 + 4 * i + r4;
+            if (mr < p.M) rnext[i] = __ldg(reinterpret_cast<const float4*>(rbase + (size_t)mr * p.ldo + n0) + c4);
+          }
         }
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       int b_idx = 0, t_idx = 0;
-      if (p.epi == EPI_QKV && live) { b_idx = m / p.T; t_idx = m - b_idx * p.T; }
+      if (kEpi == EPI_QKV && live) { b_idx = m / p.T; t_idx = m - b_idx * p.T; }
+      size_t qk_row[4];                               // EPI_QKV: (b*heads*T + t) of the four rows this lane writes back
+      if (kEpi == EPI_QKV) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mr = min(m0 + 8 * i + r8, p.M - 1);
+          const int bb = mr / p.T;
+          qk_row[i] = (size_t)bb * p.heads * p.T + (mr - bb * p.T);
+        }
+      }
 #pragma unroll 1
       for (int c = c_beg; c < c_end; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
         const int n0 = n_blk * BN + c * 32;
-        float4 rcur[8];
-        if (p.epi == EPI_RESID_F32) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          const int n1 = n0 + 32;
-          if (c + 1 < c_end && live && n1 < p.N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + n1) + i);
-          }
-        }
         tc_wait_ld();
-        if (live && n0 < p.N) {
+        if (n0 < p.N) {                                 // warp-uniform
           float f[32];
           if (p.bias) {
 #pragma unroll
@@ -253,37 +248,72 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
           }
-          if (p.epi == EPI_F16) {
-            store_f16x32(reinterpret_cast<__half*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0, f);
-          } else if (p.epi == EPI_GELU_F16) {
+          const int which = kEpi == EPI_QKV ? n0 / C : 0;
+          if (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
+            // ---- fp32 out: rows of 128 bytes
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-            store_f16x32(reinterpret_cast<__half*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0, f);
-          } else if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + bi * p.out_bstride + (size_t)m * p.ldo + n0);
-            if (p.epi == EPI_RESID_F32) {
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(st32 + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            __syncwarp();
+            float* obase = reinterpret_cast<float*>(p.out) + bi * p.out_bstride;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 r = rcur[i];
-                o4[i] = make_float4(r.x + f[4 * i], r.y + f[4 * i + 1], r.z + f[4 * i + 2], r.w + f[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + r4, mr = m0 + rr;
+              float4 o = *reinterpret_cast<const float4*>(st32 + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+              if (kEpi == EPI_RESID_F32) {
+                const float4 r = rnext[i];
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                // this slot's value is consumed: start the same row's load for the next chunk right away
+                if (c + 1 < c_end && n0 + 32 < p.N && mr < p.M)
+                  rnext[i] = __ldg(reinterpret_cast<const float4*>(rbase + (size_t)mr * p.ldo + n0 + 32) + c4);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              if (mr < p.M) *(reinterpret_cast<float4*>(obase + (size_t)mr * p.ldo + n0) + c4) = o;
             }
-          } else {  // EPI_QKV: scatter to Q [B,h,T,64], K [B,h,T,64], V^T [B,h,64,Tpad]
-            const int which = n0 / C;
-            const int cc = n0 - which * C;
-            const int h = cc >> 6, d0 = cc & 63;
-            const size_t bh = (size_t)b_idx * p.heads + h;
-            if (which < 2) {
-              __half* dst = (which == 0 ? p.q : p.k) + (bh * p.T + t_idx) * 64 + d0;
-              store_f16x32(dst, f);
-            } else {
+            __syncwarp();
+          } else if (kEpi == EPI_QKV && which == 2) {
+            // ---- V^T [B,h,64,Tpad]: consecutive lanes = consecutive tokens, already 64 contiguous bytes per store
+            if (live) {
+              const int cc = n0 - which * C;
+              const int h = cc >> 6, d0 = cc & 63;
+              const size_t bh = (size_t)b_idx * p.heads + h;
               __half* dst = p.vt + (bh * 64 + d0) * (size_t)p.Tpad + t_idx;
 #pragma unroll
               for (int i = 0; i < 32; ++i) dst[(size_t)i * p.Tpad] = __float2half_rn(f[i]);
             }
+          } else {
+            // ---- fp16 out (plain, GELU, Q / K head split): rows of 64 bytes
+            if (kEpi == EPI_GELU_F16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+            }
+            uint4* st16 = reinterpret_cast<uint4*>(st32);      // row r at 64 r bytes, piece c at position c ^ ((r >> 1) & 3)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+              __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+              __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+              __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+              st16[lane * 4 + (i ^ ((lane >> 1) & 3))] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + r8, mr = m0 + rr;
+              const uint4 o = st16[rr * 4 + (c8 ^ ((rr >> 1) & 3))];
+              if (mr < p.M) {
+                __half* dst;
+                if (kEpi == EPI_QKV) {
+                  const int cc = n0 - which * C;
+                  const int h = cc >> 6, d0 = cc & 63;
+                  dst = (which == 0 ? p.q : p.k) + (qk_row[i] + (size_t)h * p.T) * 64 + d0;
+                } else {
+                  dst = reinterpret_cast<__half*>(p.out) + bi * p.out_bstride + (size_t)mr * p.ldo + n0;
+                }
+                *(reinterpret_cast<uint4*>(dst) + c8) = o;
+              }
+            }
+            __syncwarp();
           }
         }
       }
@@ -325,28 +355,42 @@ int launch_linear(const void* x, const void* w, long long x_rows_per_batch, long
     int dev;
     AS_CUDA(cudaGetDevice(&dev));
     AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    AS_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AS_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
-  if (num_m == 1) {
+  const void* fn = nullptr;
+  const bool pair = num_m > 1;
+#define AS_PICK(E)                                                                                   \
+  case E: fn = pair ? (const void*)linear_tcgen05_kernel<2, E> : (const void*)linear_tcgen05_kernel<1, E>; break;
+  switch (p.epi) {
+    AS_PICK(EPI_F16) AS_PICK(EPI_GELU_F16) AS_PICK(EPI_RESID_F32) AS_PICK(EPI_QKV) AS_PICK(EPI_F32)
+    default: return AS_ERR_BAD_ARG;
+  }
+#undef AS_PICK
+  static bool attr_done[2][8] = {};
+  if (!attr_done[pair][p.epi]) {
+    AS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done[pair][p.epi] = true;
+  }
+  void* args[] = {(void*)&tm_a, (void*)&tm_b, (void*)&p};
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (!pair) {
     const int tiles = num_n * p.batch;
-    linear_tcgen05_kernel<1><<<tiles < num_sms ? tiles : num_sms, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+    cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+    cfg.numAttrs = 0;
   } else {
     const int tiles = ((num_m + 1) / 2) * num_n * p.batch;       // cluster tiles
     const int max_clusters = num_sms / 2;
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (tiles < max_clusters ? tiles : max_clusters));
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AS_CUDA(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<2>, tm_a, tm_b, p));
   }
+  AS_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   AS_LAUNCH_CHECK();
   return 0;
 }
