@@ -23,6 +23,7 @@ from . import lib as _l
 from . import ops
 
 PATCH = 16
+SEED_LEVELS = 4          # threshold-doubling rounds of the seed sampling answered by one counting pass
 
 
 # --------------------------------------------------------------------------------------------------- RNG front ends
@@ -326,14 +327,16 @@ def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=
     st.update(cam_low=cam_low, cam_mm=cam_mm, hp=hp, wp=wp)
     n_items = st['n_items']
 
-    def count(d_thr):
-        rc = torch.empty(n_items, H, device=dev, dtype=torch.int32)
+    def count(d_thr, levels=1):
+        rc = torch.empty(levels, n_items, H, device=dev, dtype=torch.int32)
         _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(st['d_kind']), _p(st['d_a']), _p(st['d_b']), _p(d_thr), n_items,
-                                    hp, wp, _p(rc), _sp()), 'as_norm_rowcount')
-        return rc, d_thr, _Pending(rc.sum(1, dtype=torch.int32))
+                                    hp, wp, levels, _p(rc), _sp()), 'as_norm_rowcount')
+        return rc, d_thr, _Pending(rc.sum(2, dtype=torch.int32))
 
     st['count'] = count
-    st['rowcnt'], st['d_thr'], st['pending'] = count(st['d_thr'])
+    # one pass counts for thr, 2 thr, 4 thr, 8 thr: the first rounds of the reference's threshold-doubling loop need no
+    # second kernel (and no second trip to the host)
+    st['rowcnt'], st['d_thr'], st['pending'] = count(st['d_thr'], SEED_LEVELS)
     return st
 
 
@@ -354,14 +357,26 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
     d_kind, d_a, d_b = st['d_kind'], st['d_a'], st['d_b']
     P = num_points
     rowcnt, d_thr = st['rowcnt'], st['d_thr']
-    totals = st['pending'].get().numpy().astype(np.int64)      # host sync (1) -- normally already satisfied
+    lv_tot = st['pending'].get().numpy().astype(np.int64)      # host sync (1) -- normally already satisfied; [levels, n_items]
     np_kind, np_a, np_row = st['np_kind'], st['np_a'], st['np_row']
-    # bg candidates too few -> the reference doubles the threshold until there are enough (RH:360-364)
-    factor = np.ones(n_items)
+    # bg candidates too few -> the reference doubles the threshold until there are enough (RH:360-364): take the first
+    # counted level that has enough; only if even the last one falls short do the doubling rounds continue on the device
+    n_lv = lv_tot.shape[0]
+    enough = (lv_tot >= P) | (np_kind == 1)[None, :]
+    level = np.where(enough.any(0), enough.argmax(0), n_lv - 1)
+    totals = lv_tot[level, np.arange(n_items)]
+    factor = np.exp2(level).astype(np.float64)
+    if n_lv == 1 or not (level > 0).any():
+        rowcnt = rowcnt[0]
+    else:
+        d_level, = _upload_i32([level], dev)
+        rowcnt = rowcnt[d_level.long(), torch.arange(n_items, device=dev)]       # [n_items, H] rows of the chosen levels
+        d_thr = _f32((np.array(thr) * factor).tolist(), dev)
     while ((np_kind != 1) & (totals < P)).any():
         factor[(np_kind != 1) & (totals < P)] *= 2
         rowcnt, d_thr, pend = st['count'](_f32((np.array(thr) * factor).tolist(), dev))
-        totals = pend.get().numpy().astype(np.int64)
+        rowcnt = rowcnt[0]
+        totals = pend.get().numpy().astype(np.int64)[0]
     short = (np_kind == 1) & (totals < P)                    # RH:354-358: all candidates, then the GT point repeated
     if hasattr(rng, 'draws'):
         ks = rng.draws(st['keys'], P).astype(np.int64) % np.maximum(totals, 1)[:, None]       # randint(num)[:P]

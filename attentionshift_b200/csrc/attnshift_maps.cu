@@ -66,23 +66,44 @@ __device__ __forceinline__ float norm_value(const NormCtx& c, int o, int y, int 
   const float mn = c.mm[2 * o];
   return __fdiv_rn(__fsub_rn(v, mn), __fsub_rn(c.mm[2 * o + 1], mn));      // RH:333 (no epsilon)
 }
-__device__ __forceinline__ bool norm_pred(const NormCtx& c, int item, int y, int x) {
-  const int kind = c.item_kind[item];
-  const float thr = c.item_thr[item];
-  if (kind == 0) return norm_value(c, c.item_a[item], y, x) < thr;
-  if (kind == 1) return norm_value(c, c.item_a[item], y, x) >= thr;
+// value the item's predicate compares with its threshold (kind 2: mean over the image's instances, torch: sum / n)
+__device__ __forceinline__ float norm_item_value(const NormCtx& c, int item, int y, int x) {
+  if (c.item_kind[item] != 2) return norm_value(c, c.item_a[item], y, x);
   float s = norm_value(c, c.item_a[item], y, x);
   for (int o = c.item_a[item] + 1; o < c.item_b[item]; ++o) s = __fadd_rn(s, norm_value(c, o, y, x));
-  return __fdiv_rn(s, (float)(c.item_b[item] - c.item_a[item])) < thr;   // torch: sum over dim 0 then / n
+  return __fdiv_rn(s, (float)(c.item_b[item] - c.item_a[item]));
 }
-// grid (H, n_items)
-__global__ void norm_rowcount(NormCtx c, int* __restrict__ rowcnt) {
+__device__ __forceinline__ bool norm_pred(const NormCtx& c, int item, int y, int x) {
+  const float v = norm_item_value(c, item, y, x), thr = c.item_thr[item];
+  return c.item_kind[item] == 1 ? v >= thr : v < thr;
+}
+// grid (H, n_items).  rowcnt [n_levels][n_items][H]: level l counts with the threshold doubled l times (the reference doubles
+// a background threshold until enough candidates exist, RH:360-364: one pass answers the first n_levels rounds of that
+// loop; foreground thresholds never move, their levels repeat level 0)
+constexpr int NORM_MAX_LEVELS = 4;
+__global__ void norm_rowcount(NormCtx c, int n_levels, int* __restrict__ rowcnt) {
   __shared__ int red[8];
   const int y = blockIdx.x, item = blockIdx.y, W = c.wp * 16;
-  int cnt = 0;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) cnt += norm_pred(c, item, y, x);
-  cnt = block_sum_i(cnt, red);
-  if (threadIdx.x == 0) rowcnt[(size_t)item * gridDim.x + y] = cnt;
+  const bool fg = c.item_kind[item] == 1;
+  const float thr = c.item_thr[item];
+  int cnt[NORM_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < NORM_MAX_LEVELS; ++l) cnt[l] = 0;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const float v = norm_item_value(c, item, y, x);
+    float t = thr;
+#pragma unroll
+    for (int l = 0; l < NORM_MAX_LEVELS; ++l) {
+      cnt[l] += fg ? (v >= thr) : (v < t);
+      t = __fmul_rn(t, 2.f);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < NORM_MAX_LEVELS; ++l) {
+    if (l >= n_levels) break;
+    const int tot = block_sum_i(cnt[l], red);
+    if (threadIdx.x == 0) rowcnt[((size_t)l * gridDim.y + item) * gridDim.x + y] = tot;
+  }
 }
 // one warp per selection: the k-th pixel (row-major) of item that satisfies the predicate
 __global__ void norm_select(NormCtx c, const int* __restrict__ rowcnt, const int* __restrict__ sel_item,
@@ -438,11 +459,12 @@ __global__ void erode_down(const float* __restrict__ map_fg, int H, int W, float
 
 // ---- seed sampling support -------------------------------------------------------------------------------------
 extern "C" int as_norm_rowcount(const float* low, const float* minmax, const int* item_kind, const int* item_a,
-                                const int* item_b, const float* item_thr, int n_items, int hp, int wp, int* rowcnt,
-                                cudaStream_t stream) {
+                                const int* item_b, const float* item_thr, int n_items, int hp, int wp, int n_levels,
+                                int* rowcnt, cudaStream_t stream) {
   if (n_items <= 0) return 0;
+  if (n_levels < 1 || n_levels > NORM_MAX_LEVELS) return AS_ERR_BAD_ARG;
   NormCtx c{low, minmax, item_kind, item_a, item_b, item_thr, hp, wp};
-  norm_rowcount<<<dim3(hp * 16, n_items), 256, 0, stream>>>(c, rowcnt);
+  norm_rowcount<<<dim3(hp * 16, n_items), 256, 0, stream>>>(c, n_levels, rowcnt);
   AS_LAUNCH_CHECK();
   return 0;
 }

@@ -733,6 +733,7 @@ constexpr int HM2_SMEM_TILES = 2 * HM2_STAGES * TILE_BYTES;
 constexpr int HM2_WSTAGE = 32 * 33;                          // floats per math warp: its 32 x 32 result, odd row stride
 constexpr int HM2_SMEM = HM2_SMEM_TILES + 1024 + 256 + HM_MAX_HEADS * BQ * 8 + (HM_MATH / 32) * HM2_WSTAGE * 4;
 
+template <int POLY>      // POLY of every 32 exponentials run on the FMA pipe (ex2_poly) instead of MUFU
 __global__ void __launch_bounds__(HM_THREADS, 1)
 attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const HmParams p,
                       const int n_tiles, const int tiles_per_cta) {
@@ -836,8 +837,10 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[tb]);       // S_h is in registers: a later head's MMA may overwrite the buffer
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          acc[i] = fmaf(ex2_approx(fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow)), inv_l, acc[i]);
+        for (int i = 0; i < 32; ++i) {
+          const float x = fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow);
+          acc[i] = fmaf((i % 4 == 3 && i / 4 < POLY) ? ex2_poly(x) : ex2_approx(x), inv_l, acc[i]);
+        }
       }
       // results: through a per-warp staging tile (no block barrier, the stores drain under the next tile's exponentials)
       // so that every global store instruction writes whole 64 / 128-byte runs
@@ -973,7 +976,9 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
     AS_CUDA(cudaGetDevice(&dev));
     AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     AS_CUDA(cudaFuncSetAttribute(attn_headmean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
     attr = true;
   }
   HmParams p;
@@ -986,7 +991,11 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
     const int n_tiles = nt * nt * B;
     const int per = (n_tiles + num_sms - 1) / num_sms;
     const int grid = (n_tiles + per - 1) / per;
-    attn_headmean2_kernel<<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
+    static int poly = -1;
+    if (poly < 0) { const char* e = getenv("AS_HEADMEAN_POLY"); poly = e ? atoi(e) : 0; }
+    if (poly == 4) attn_headmean2_kernel<4><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
+    else if (poly == 8) attn_headmean2_kernel<8><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
+    else attn_headmean2_kernel<0><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
   } else if (rowsum_slices == 1) {
     attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
   } else {

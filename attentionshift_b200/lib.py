@@ -45,7 +45,7 @@ SIGNATURES = {
     'as_cam_minmax': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     'as_cam_bbox_workspace': (_sz, [_i, _i, _i]),
     'as_cam_bbox': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
-    'as_norm_rowcount': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'as_norm_rowcount': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     'as_norm_select': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'as_seed_proto': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'as_refine_threshold': (_i, [_vp, _i, _i, _f, _vp, _vp]),

@@ -198,20 +198,25 @@ def run_ours(args):
             bufs[i % 2].copy_(img_host, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
-    barrier()
+    def e2e_loop(n):
+        d2h = 0
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            res = one_step(bb, head, bufs[i % 2], inputs, True)
+            freed[i % 2].record()
+            d2h = sum(m.nbytes for m in res['pseudo_gt_masks'])
+        return d2h
+
     for f in freed:
         f.record()
+    e2e_loop(max(args.warmup, 1))          # untimed: first use of the pinned mask buffers / copy stream (cudaHostAlloc is slow)
+    barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    d2h = 0
-    prefetch(0)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            prefetch(i + 1)
-        torch.cuda.current_stream().wait_event(ready[i % 2])
-        res = one_step(bb, head, bufs[i % 2], inputs, True)
-        freed[i % 2].record()
-        d2h = sum(m.nbytes for m in res['pseudo_gt_masks'])
+    d2h = e2e_loop(args.steps)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps

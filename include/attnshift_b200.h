@@ -108,8 +108,10 @@ int as_cosine_maps(const float* feats, long long feat_img_stride, int n_img, int
 
 /* ------------------------------------------------------------------ refined instance maps (RH:1000-1046, RH:668-707) */
 
+/* rowcnt [n_levels][n_items][H] (n_levels <= 4): level l = per-row candidate counts with the item's threshold doubled l
+ * times (RH:360-364 doubles background thresholds until there are enough candidates; foreground levels repeat level 0). */
 int as_norm_rowcount(const float* low, const float* minmax, const int* item_kind, const int* item_a, const int* item_b,
-                     const float* item_thr, int n_items, int hp, int wp, int* rowcnt, as_stream_t stream);
+                     const float* item_thr, int n_items, int hp, int wp, int n_levels, int* rowcnt, as_stream_t stream);
 int as_norm_select(const float* low, const float* minmax, const int* item_kind, const int* item_a, const int* item_b,
                    const float* item_thr, int hp, int wp, const int* rowcnt, const int* sel_item, const int* sel_k,
                    int n_sel, int* out_xy, as_stream_t stream);
