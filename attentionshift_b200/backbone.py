@@ -76,7 +76,7 @@ class VisionTransformerDet(nn.Module):
                  recompute_last_feat=False, point_tokens_num=100, num_classes=20, return_attention=False,
                  with_point_head=True, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=None, init_values=0,
-                 attn_layers=None, **kwargs):
+                 attn_layers=None, cuda_graph=False, **kwargs):
         super().__init__()
         assert not with_fpn or (patch_size in (8, 16))
         assert not recompute_last_feat or (last_feat and recompute_last_feat)
@@ -101,6 +101,11 @@ class VisionTransformerDet(nn.Module):
         # which layers emit their head-mean attention map; None = all (reference behaviour, VTD:236/242).
         # The attention-shift head only reads the last ``cam_layer`` = 7 (RH:2261): pass attn_layers=7 to skip the rest.
         self.attn_layers = attn_layers
+        # replay the whole forward as ONE CUDA graph (static shapes, no host synchronisation inside): the ~200 launches of a
+        # step cost the host one call, and every buffer of the forward lives in the graph's private pool.  The returned
+        # tensors are views of that pool -- valid until the next forward of the same input shape overwrites them.
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
 
         self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
         num_patches = self.patch_embed.num_patches
@@ -228,8 +233,35 @@ class VisionTransformerDet(nn.Module):
                            resid=x)
         return x, attn
 
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     @torch.no_grad()
     def forward(self, x):           # VTD:221-275
+        if not (self.cuda_graph and x.is_cuda):
+            return self._forward_eager(x)
+        key = (tuple(x.shape), x.dtype, x.device)
+        ent = self._graphs.get(key)
+        wkey = self._weights_key()
+        if ent is None or ent['wkey'] != wkey:              # first call for this shape, or the weights changed
+            static_in = torch.empty_like(x, memory_format=torch.contiguous_format)
+            static_in.copy_(x)
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                   # warm-up outside the capture: lazy one-time work (attribute
+                self._forward_eager(static_in)              # setting, fp16 weight copies) must not land in the graph
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(static_in)
+            ent = dict(graph=graph, static_in=static_in, out=out, wkey=wkey)
+            self._graphs[key] = ent
+        ent['static_in'].copy_(x, non_blocking=True)
+        ent['graph'].replay()
+        return ent['out']
+
+    @torch.no_grad()
+    def _forward_eager(self, x):
         B, _, H, W = x.shape
         Hp, Wp = H // self.patch_size, W // self.patch_size
         tok = self.prepare_tokens(x)

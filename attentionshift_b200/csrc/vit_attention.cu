@@ -261,7 +261,8 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 //     for P V of the previous tile after they have already computed half of the new probabilities
 //   * K and V^T have separate rings: a K stage is free again after Q K^T, one tile earlier than V^T
 //   * packed fp32x2 FMA / ADD (FFMA2 / FADD2) halve the issue slots of the logit scaling and the row sums
-//   * POLY pairs of every 16-pair chunk take exp2 on the FMA pipe (ex2_poly) instead of MUFU
+//   * POLY pairs of every 16-pair chunk take exp2 on the FMA pipe (packed ex2_poly2) instead of MUFU: with the FMNMX
+//     chain of the window test gone (MODE 1) a quarter of the exponentials fits into the freed issue slots
 constexpr int FWD2_SMEM = 5 * TILE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
@@ -277,10 +278,33 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float lo32f(uint64_t v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float hi32f(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
-template <int POLY>
+// ex2_poly (common.cuh) for a packed pair: the range reduction and the degree-4 polynomial run as FADD2 / FFMA2
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+  const float x0 = fmaxf(lo32f(x2), -126.f), x1 = fmaxf(hi32f(x2), -126.f);
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const uint64_t fl = fadd2(x, magic);                       // integer part in the low mantissa bits
+  const uint64_t ni = fadd2(fl, nmagic);                     // round(x)
+  const uint64_t f = ffma2(ni, pack2(-1.f, -1.f), x);        // x - round(x), |f| <= 0.5
+  uint64_t q = ffma2(pack2(0.009676037356257439f, 0.009676037356257439f), f, pack2(0.05592203512787819f, 0.05592203512787819f));
+  q = ffma2(q, f, pack2(0.2402210682630539f, 0.2402210682630539f));
+  q = ffma2(q, f, pack2(0.6931210160255432f, 0.6931210160255432f));
+  q = ffma2(q, f, pack2(1.0000001192092896f, 1.0000001192092896f));
+  p0 = __int_as_float(__float_as_int(lo32f(q)) + (__float_as_int(lo32f(fl)) << 23));
+  p1 = __int_as_float(__float_as_int(hi32f(q)) + (__float_as_int(hi32f(fl)) << 23));
+}
+
+template <int POLY, int MODE>   // MODE 0: window test on the raw logits of every chunk (FMNMX), S released before the last
+                                // chunk's exponentials; MODE 1: no max at all -- the row sum of the tile tells afterwards
+                                // whether any probability left the fp16-safe range (sum < 2^15), S released after that test
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
@@ -412,24 +436,26 @@ mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           uint32_t (&nxt)[32] = (c & 1) ? va : vb;
           tc_wait_ld();
           if (c < 3) tmem_ld_32x32(lane_addr + COL_S + (c + 1) * 32, nxt);
-          float mx = fmaxf(__uint_as_float(cur[0]), __uint_as_float(cur[1]));
-          float mxb = fmaxf(__uint_as_float(cur[2]), __uint_as_float(cur[3]));
+          if (MODE == 0) {
+            float mx = fmaxf(__uint_as_float(cur[0]), __uint_as_float(cur[1]));
+            float mxb = fmaxf(__uint_as_float(cur[2]), __uint_as_float(cur[3]));
 #pragma unroll
-          for (int i = 4; i < 32; i += 4) {
-            mx = fmaxf(mx, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
-            mxb = fmaxf(mxb, fmaxf(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
-          }
-          if (__any_sync(0xffffffffu, fmaxf(mx, mxb) > lim)) { slow = true; break; }
-          if (c == 3) {                                     // S is in registers and inside the window: release it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
+            for (int i = 4; i < 32; i += 4) {
+              mx = fmaxf(mx, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+              mxb = fmaxf(mxb, fmaxf(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
+            }
+            if (__any_sync(0xffffffffu, fmaxf(mx, mxb) > lim)) { slow = true; break; }
+            if (c == 3) {                                   // S is in registers and inside the window: release it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_empty);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint64_t x = ffma2((uint64_t)cur[2 * i] | ((uint64_t)cur[2 * i + 1] << 32), c2, nm2);
             float p0, p1;
-            if (i < POLY) { p0 = ex2_poly(lo32f(x)); p1 = ex2_poly(hi32f(x)); }
+            if (i < POLY) ex2_poly2(x, p0, p1);
             else { p0 = ex2_approx(lo32f(x)); p1 = ex2_approx(hi32f(x)); }
             if (i & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
             __half2 hh = __floats2half2_rn(p0, p1);
@@ -441,9 +467,23 @@ mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tmem_st_32x32(lane_addr + COL_P + (c >> 1) * 32, pk);
           }
         }
-        if (!slow) {
+        if (MODE == 0) {
+          if (!slow) {
+            const uint64_t a = fadd2(acc0, acc1);
+            l_run += lo32f(a) + hi32f(a);
+          }
+        } else {
           const uint64_t a = fadd2(acc0, acc1);
-          l_run += lo32f(a) + hi32f(a);
+          const float tot = lo32f(a) + hi32f(a);
+          // every probability of the tile is below its row sum: sum < 2^15 means nothing came near the fp16 limit (2^16)
+          if (__any_sync(0xffffffffu, !(tot < 32768.f))) {
+            slow = true;                                    // S is still intact: the exact two-pass tile below redoes it
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+            l_run += tot;
+          }
         }
       }
       if (slow) {
@@ -733,7 +773,6 @@ constexpr int HM2_SMEM_TILES = 2 * HM2_STAGES * TILE_BYTES;
 constexpr int HM2_WSTAGE = 32 * 33;                          // floats per math warp: its 32 x 32 result, odd row stride
 constexpr int HM2_SMEM = HM2_SMEM_TILES + 1024 + 256 + HM_MAX_HEADS * BQ * 8 + (HM_MATH / 32) * HM2_WSTAGE * 4;
 
-template <int POLY>      // POLY of every 32 exponentials run on the FMA pipe (ex2_poly) instead of MUFU
 __global__ void __launch_bounds__(HM_THREADS, 1)
 attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const HmParams p,
                       const int n_tiles, const int tiles_per_cta) {
@@ -821,13 +860,14 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         asm volatile("bar.sync 1, %0;" ::"n"(HM_MATH) : "memory");
       }
-      float acc[32];
+      uint64_t acc2[16];                               // packed fp32 pairs: FFMA2 halves the issue slots around the MUFU
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 16; ++i) acc2[i] = 0ull;
+      const uint64_t c2 = pack2(p.scale_log2, p.scale_log2);
       for (int h = 0; h < p.heads; ++h, ++g) {
         const uint32_t tb = g % HM2_NBUF;
         const float2 mlv = ml_s[h * BQ + row];
-        const float mrow = mlv.x, inv_l = mlv.y;
+        const uint64_t nm2 = pack2(-mlv.x, -mlv.x), il2 = pack2(mlv.y, mlv.y);
         mbar_wait(&s_full[tb], (g / HM2_NBUF) & 1);
         tc_fence_after();
         uint32_t v0[32];
@@ -837,11 +877,15 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[tb]);       // S_h is in registers: a later head's MMA may overwrite the buffer
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fmaf(__uint_as_float(v0[i]), p.scale_log2, -mrow);
-          acc[i] = fmaf((i % 4 == 3 && i / 4 < POLY) ? ex2_poly(x) : ex2_approx(x), inv_l, acc[i]);
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t x = ffma2((uint64_t)v0[2 * i] | ((uint64_t)v0[2 * i + 1] << 32), c2, nm2);
+          // (moving a share of these exponentials to the FMA pipe, as the forward kernel does, was measured: no gain here)
+          acc2[i] = ffma2(pack2(ex2_approx(lo32f(x)), ex2_approx(hi32f(x))), il2, acc2[i]);
         }
       }
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { acc[2 * i] = lo32f(acc2[i]); acc[2 * i + 1] = hi32f(acc2[i]); }
       // results: through a per-warp staging tile (no block barrier, the stores drain under the next tile's exponentials)
       // so that every global store instruction writes whole 64 / 128-byte runs
       const int c0 = kt * BKV + cslice * 32;
@@ -906,15 +950,16 @@ int g_mhsa_variant = -1;
 int mhsa_variant() {
   if (g_mhsa_variant < 0) {
     const char* e = getenv("AS_MHSA_VARIANT");
-    g_mhsa_variant = e ? atoi(e) : 2;
+    g_mhsa_variant = e ? atoi(e) : 4;
   }
   return g_mhsa_variant;
 }
 
 }  // namespace
 
-// Schedule of the attention forward: 1 = first-generation kernel (two passes over S per tile), 2 = single-pass schedule
-// (default), 3 / 4 = single-pass with 1/8 resp. 1/4 of the exponentials on the FMA pipe.  Also: env AS_MHSA_VARIANT.
+// Schedule of the attention forward: 1 = first-generation kernel (two passes over S per tile), 2 = single pass with a window
+// test per chunk, 3 = single pass with the row-sum test, 4 (default) = 3 with a quarter of the exponentials on the FMA pipe
+// (measured at B=8, T=4197, 12 heads: 0.68 / 0.60 / 0.61 / 0.55 ms).  Also: env AS_MHSA_VARIANT.
 extern "C" int as_mhsa_set_variant(int v) {
   if (v < 1 || v > 4) return AS_ERR_BAD_ARG;
   g_mhsa_variant = v;
@@ -937,9 +982,9 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
   static bool attr = false;
   if (!attr) {
     AS_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_fwd2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
     attr = true;
   }
   FwdParams p;
@@ -949,9 +994,9 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
   const dim3 grid((T + BQ - 1) / BQ, heads, B);
   switch (mhsa_variant()) {
     case 1: mhsa_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
-    case 3: mhsa_fwd2_kernel<2><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
-    case 4: mhsa_fwd2_kernel<4><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
-    default: mhsa_fwd2_kernel<0><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    case 3: mhsa_fwd2_kernel<0, 1><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    default: mhsa_fwd2_kernel<4, 1><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
+    case 2: mhsa_fwd2_kernel<0, 0><<<grid, FWD_THREADS, FWD2_SMEM, stream>>>(tm_q, tm_k, tm_v, p); break;
   }
   AS_LAUNCH_CHECK();
   return 0;
@@ -976,9 +1021,7 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
     AS_CUDA(cudaGetDevice(&dev));
     AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     AS_CUDA(cudaFuncSetAttribute(attn_headmean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
-    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(attn_headmean2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM2_SMEM));
     attr = true;
   }
   HmParams p;
@@ -991,11 +1034,7 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
     const int n_tiles = nt * nt * B;
     const int per = (n_tiles + num_sms - 1) / num_sms;
     const int grid = (n_tiles + per - 1) / per;
-    static int poly = -1;
-    if (poly < 0) { const char* e = getenv("AS_HEADMEAN_POLY"); poly = e ? atoi(e) : 0; }
-    if (poly == 4) attn_headmean2_kernel<4><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
-    else if (poly == 8) attn_headmean2_kernel<8><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
-    else attn_headmean2_kernel<0><<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
+    attn_headmean2_kernel<<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
   } else if (rowsum_slices == 1) {
     attn_headmean_kernel<<<dim3(nt, nt, B), HM_THREADS, HM_SMEM, stream>>>(tm_q, tm_k, p);
   } else {

@@ -25,6 +25,9 @@ SIGNATURES = {
     'as_mhsa_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_set_variant': (_i, [_i]),
     'as_mt19937_draws': (_i, [_vp, _i, _i, _vp]),
+    'as_timer_slots': (_i, []),
+    'as_timer_record': (_i, [_i, _i, _vp]),
+    'as_timer_elapsed': (_i, [_i, _vp]),
     'as_attn_headmean': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
     'as_bgemm_f16_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _f, _vp]),
     'as_rollout_tc_workspace': (_sz, [_i, _i, _i]),
@@ -66,35 +69,67 @@ _lib = None
 
 
 class _Timers:
-    """Optional per-entry-point CUDA-event timing (bench.py): events are recorded on the launching stream around each
-    C-ABI call, so a family's time is the device time of the kernels that call enqueued."""
+    """Optional per-entry-point device timing (bench.py).  Every C-ABI call is bracketed by one of the library's timing slots
+    (as_timer_record) on the launching stream.  Calls made while the stream is being captured keep their slot for good -- the
+    replayed graph re-records it every step -- while the slots of live calls are recycled at every ``begin_step()``.
+    ``summary()`` adds up the last step: device time per entry point = the kernels that call enqueued."""
 
     def __init__(self):
         self.on = False
-        self.events = {}
+        self.captured = []          # (name, slot) of calls that live inside a CUDA graph
+        self.live = []              # (name, slot) of this step's eager calls
+        self.next_captured = 0
+        self.next_live = 0
 
     def enable(self):
         self.on = True
-        self.events = {}
+        self.captured, self.live = [], []
+        self.next_captured = 0
+        load()
+        self.n_slots = _lib._cdll.as_timer_slots()
+        self.next_live = self.n_slots // 2
 
     def disable(self):
         self.on = False
 
+    def begin_step(self):
+        self.live = []
+        self.next_live = self.n_slots // 2
+
     def wrap(self, name, fn):
         def call(*a):
-            if not self.on:
+            if not self.on or name.startswith('as_timer') or name == 'as_mt19937_draws':
                 return fn(*a)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                slot = self.next_captured
+                self.next_captured += 1
+                assert slot < self.n_slots // 2, 'timing slots exhausted'
+                self.captured.append((name, slot))
+            else:
+                slot = self.next_live
+                self.next_live += 1
+                if slot >= self.n_slots:
+                    return fn(*a)
+                self.live.append((name, slot))
+            sp = stream_ptr()
+            _lib._cdll.as_timer_record(slot, 0, sp)
             r = fn(*a)
-            e.record()
-            self.events.setdefault(name, []).append((s, e))
+            _lib._cdll.as_timer_record(slot, 1, sp)
             return r
         return call
 
     def summary(self):
+        """{entry point: dict(ms = device time in the last step, n = calls)}."""
         torch.cuda.synchronize()
-        return {k: dict(ms=sum(s.elapsed_time(e) for s, e in v), n=len(v)) for k, v in self.events.items()}
+        out = {}
+        ms = ctypes.c_float()
+        for name, slot in self.captured + self.live:
+            if _lib._cdll.as_timer_elapsed(slot, ctypes.byref(ms)) == 0:
+                d = out.setdefault(name, dict(ms=0.0, n=0))
+                d['ms'] += ms.value
+                d['n'] += 1
+        return out
 
 
 TIMERS = _Timers()

@@ -31,7 +31,9 @@ def qkv_proj(x, w, bias, B, T, heads, Tpad):
     L = _l.load()
     q = torch.empty(B, heads, T, 64, device=x.device, dtype=torch.float16)
     k = torch.empty_like(q)
-    vt = torch.zeros(B, heads, 64, Tpad, device=x.device, dtype=torch.float16)
+    vt = torch.empty(B, heads, 64, Tpad, device=x.device, dtype=torch.float16)
+    if Tpad > T:
+        vt[..., T:].zero_()             # only the padding columns: P V multiplies them (by zero probabilities), NaNs must not sit there
     _l.check(L.as_qkv_proj_f16(_l.ptr(x), _l.ptr(w), _l.ptr(bias), _l.ptr(q), _l.ptr(k), _l.ptr(vt), B, T, Tpad, heads,
                                _l.stream_ptr()), 'as_qkv_proj_f16')
     return q, k, vt

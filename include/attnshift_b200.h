@@ -47,8 +47,9 @@ int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float* bias, voi
 int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m, float* l, int B, int T, int Tpad,
                 int heads, as_stream_t stream);
 
-/* Schedule of as_mhsa_fwd (no reference counterpart; benchmarking aid): 1 = two passes over S per tile, 2 = single-pass
-   schedule (default), 3 / 4 = single pass with 1/8 resp. 1/4 of the exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
+/* Schedule of as_mhsa_fwd (no reference counterpart; benchmarking aid): 1 = two passes over S per tile, 2 = single pass
+   with a window test per chunk, 3 = single pass with a row-sum test after the tile, 4 (default) = 3 with a quarter of the
+   exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
 int as_mhsa_set_variant(int variant);
 
 /* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] partial row sums in
@@ -182,6 +183,14 @@ int as_merge_prototypes(const float* proto, const int* keep, int n_tot, int S, i
 int as_part_centers(const float* pmap, const int* n_parts, const float* rois, const float* feats,
                     long long feat_img_stride, const int* obj_img, int n_tot, int S, int N, int C, int wp, int KP,
                     float* centers, int* valid, int* part_id, float* cfeat, float* stat_scratch, as_stream_t stream);
+
+/* ------------------------------------------------------------------ timing slots (measurement aid, no reference counterpart)
+ * Event pairs owned by the library: as_timer_record(slot, 0 / 1, stream) marks the start / end of an interval on the stream;
+ * inside a stream capture the records become external event nodes, so a replayed CUDA graph re-times its kernels on every
+ * replay.  as_timer_elapsed reads the last interval of a slot (synchronise the stream first). */
+int as_timer_slots(void);
+int as_timer_record(int slot, int which, as_stream_t stream);
+int as_timer_elapsed(int slot, float* ms);
 
 /* ------------------------------------------------------------------ host-side RNG helper (no device work)
  * First k (<= 624) raw 32-bit outputs of at::mt19937 seeded like torch.Generator().manual_seed(seed), per key:

@@ -59,4 +59,4 @@ for std in (0.6, 1.5):
         L.as_mhsa_set_variant(v)
         ms = timeit(lambda: ops.mhsa_fwd(q, k, vt, T))
         print(f'std {std} variant {v}: {ms:7.3f} ms   {4 * T * T * 768 * B / ms / 1e9:7.1f} TFLOP/s', flush=True)
-L.as_mhsa_set_variant(2)
+L.as_mhsa_set_variant(4)

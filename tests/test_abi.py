@@ -33,7 +33,7 @@ def test_header_argument_counts_match_binding():
     src = open(os.path.join(ROOT, 'include', 'attnshift_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     for name, args in re.findall(r'\b(as_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
-        n = len([a for a in args.split(',') if a.strip()])
+        n = len([a for a in args.split(',') if a.strip() and a.strip() != 'void'])
         assert n == len(lib.SIGNATURES[name][1]), name
 
 

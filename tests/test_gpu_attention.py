@@ -12,7 +12,7 @@ def _ref(q, k, vt, T):
     return o, attn
 
 
-@pytest.mark.parametrize('variant', [2, 1, 4])          # attention schedules, see as_mhsa_set_variant
+@pytest.mark.parametrize('variant', [4, 3, 2, 1])          # attention schedules, see as_mhsa_set_variant
 @pytest.mark.parametrize('slices', [4, 1])              # head-mean schedules: persistent / one CTA per tile
 @pytest.mark.parametrize('B,heads,T', [(1, 2, 128), (2, 3, 297), (1, 12, 1125), (1, 2, 4197), (3, 16, 640)])
 def test_mhsa_and_headmean(B, heads, T, slices, variant):
@@ -25,7 +25,7 @@ def test_mhsa_and_headmean(B, heads, T, slices, variant):
     vt = torch.zeros(B, heads, 64, Tpad, device='cuda', dtype=torch.float16)
     vt[..., :T] = torch.randn(B, heads, 64, T, device='cuda').half()
     o, m, l = ops.mhsa_fwd(q, k, vt, T)
-    lib.load().as_mhsa_set_variant(2)
+    lib.load().as_mhsa_set_variant(4)
     ro, rattn = _ref(q, k, vt, T)
     # P is rounded to fp16 before P@V and O is stored in fp16: ~1e-3 of the output scale
     err = (o.float() - ro).abs().max().item()

@@ -54,3 +54,35 @@ def test_backbone_vs_oracle(embed, heads, depth, img):
     for a, b in zip(out['attns'], ref['attns']):
         torch.testing.assert_close(a.cpu(), b, rtol=1e-3, atol=2e-6)
     assert _rel(out['last_feat'].cpu(), ref['last_feat']) < 2e-3
+
+
+def test_cuda_graph_replay_equals_eager():
+    """cuda_graph=True replays the forward as one CUDA graph: same bits as the eager launches, for every new input, and the
+    graph is rebuilt when a weight changes."""
+    from attentionshift_b200.registry import build_backbone
+    embed, heads, depth, img, n_pt = 128, 2, 2, 224, 12
+    sd = vit_state_dict(embed, depth, heads, img, n_point_tokens=n_pt, seed=4)
+    cfg = dict(type='VisionTransformerDet', img_size=img, patch_size=16, embed_dim=embed, depth=depth, num_heads=heads,
+               mlp_ratio=4, qkv_bias=True, with_fpn=False, last_feat=True, return_attention=True, point_tokens_num=n_pt,
+               with_point_head=True, out_indices=[depth - 1])
+    eager = build_backbone(dict(cfg))
+    graph = build_backbone(dict(cfg, cuda_graph=True))
+    for m in (eager, graph):
+        m.load_state_dict(sd, strict=False)
+        m.cuda().eval()
+    gen = torch.Generator().manual_seed(2)
+    for rep in range(3):
+        x = torch.randn(2, 3, img, img, generator=gen).cuda()
+        a, b = eager(x), graph(x)
+        assert torch.equal(a['last_feat'], b['last_feat'])
+        # the point heads are torch nn.Linear (cuBLAS picks its algorithm per context): close, not bit-equal
+        torch.testing.assert_close(a['outputs_coord'], b['outputs_coord'], rtol=0, atol=2e-3)
+        for u, v in zip(a['attns'], b['attns']):
+            assert torch.equal(u, v)
+        assert b['attns'][-1]._as_rowsum_part is not None
+    assert len(graph._graphs) == 1
+    with torch.no_grad():
+        for m in (eager, graph):
+            m.blocks[0].mlp.fc1.bias.add_(0.5)
+    a, b = eager(x), graph(x)
+    assert torch.equal(a['last_feat'], b['last_feat'])
