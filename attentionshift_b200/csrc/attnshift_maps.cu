@@ -183,7 +183,7 @@ __global__ void refine_threshold(float* __restrict__ cur, int N, float tau, floa
   if (threadIdx.x == 0) wsum[blockIdx.x] = s;
 }
 // partial weighted sums: part[g][tile][s][c] = sum_{n in tile} w[g,s,n] * f[n,c].   grid (tiles, G), smem S*CC floats
-constexpr int WS_TOK = 256;
+constexpr int WS_TOK = 32;     // short tiles: the token loop of a CTA is a chain of dependent loads, parallelism comes from the grid
 __global__ void __launch_bounds__(256)
 weighted_sum_partial(const float* __restrict__ feats, long long fstride, const int* __restrict__ grp_img,
                      const float* __restrict__ w, int N, int C, int S, int CC, float* __restrict__ part) {

@@ -428,6 +428,73 @@ extern "C" int as_mean_shift(const float* feats, long long feat_img_stride, int 
 
 // Generic cosine maps: sim[g,s,n] = cos(protos[g,s,:], feats[grp_img[g], n, :])  (F.cosine_similarity semantics).
 // Used for the seed-prototype maps (RH:339), the refinement maps (RH:696) and the part maps (RH:297-301).
+// Cosine maps for a handful of seeds per group (refinement loop, part maps): one WARP per token.  The warp reads the
+// token row once (coalesced float4, the next row already in flight), takes its norm on the way, and dots it with every
+// seed of the group held in shared memory; CW_TPW consecutive tokens per warp, results parked in lane = token.
+// grid (ceil(N / CW_TOK), ceil(S / 16), G), 256 threads; C % 128 == 0, C <= 1024.
+constexpr int CW_SEEDS = 16;
+constexpr int CW_TPW = 8;                              // tokens per warp
+constexpr int CW_TOK = 8 * CW_TPW;                     // tokens per CTA
+__global__ void __launch_bounds__(256)
+cos_warp_rows(const float* __restrict__ feats, long long fstride, const int* __restrict__ grp_img, const float* __restrict__ phat,
+              int N, int C, int S, int clamp0, float* __restrict__ sim) {
+  extern __shared__ float4 ps4[];                    // [CW_SEEDS][C / 4]
+  const int g = blockIdx.z, s0 = blockIdx.y * CW_SEEDS;
+  const int ns = min(CW_SEEDS, S - s0);
+  const int c4n = C / 4, per = C / 128;              // float4 per row; float4 per lane
+  for (int i = threadIdx.x; i < ns * c4n; i += blockDim.x)
+    ps4[i] = reinterpret_cast<const float4*>(phat + ((size_t)g * S + s0) * C)[i];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int n0 = blockIdx.x * CW_TOK + warp * CW_TPW;
+  const float* fimg = feats + grp_img[g] * fstride;
+  float4 fn[8];
+  auto fetch = [&](int n) {
+    const float4* row = reinterpret_cast<const float4*>(fimg + (size_t)min(n, N - 1) * C);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) fn[i] = __ldg(row + i * 32 + lane);
+  };
+  fetch(n0);
+  __syncthreads();
+  float res[CW_SEEDS];
+#pragma unroll
+  for (int s = 0; s < CW_SEEDS; ++s) res[s] = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < CW_TPW; ++t) {
+    float4 fv[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per) {
+        fv[i] = fn[i];
+        ss += fv[i].x * fv[i].x + fv[i].y * fv[i].y + fv[i].z * fv[i].z + fv[i].w * fv[i].w;
+      }
+    if (t + 1 < CW_TPW) fetch(n0 + t + 1);
+    const float d = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
+#pragma unroll
+    for (int s = 0; s < CW_SEEDS; ++s) {
+      if (s >= ns) break;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < per) {
+          const float4 pv = ps4[s * c4n + i * 32 + lane];
+          a = fmaf(fv[i].x, pv.x, a); a = fmaf(fv[i].y, pv.y, a); a = fmaf(fv[i].z, pv.z, a); a = fmaf(fv[i].w, pv.w, a);
+        }
+      a = warp_sum(a);
+      if (lane == t) res[s] = a / d;
+    }
+  }
+  const int n = n0 + lane;
+  if (lane < CW_TPW && n < N) {
+#pragma unroll
+    for (int s = 0; s < CW_SEEDS; ++s) {
+      if (s >= ns) break;
+      sim[((size_t)g * S + s0 + s) * N + n] = clamp0 ? fmaxf(res[s], 0.f) : res[s];
+    }
+  }
+}
+
 extern "C" size_t as_cosine_maps_workspace(int n_img, int G, int S, int N, int C) {
   return (((size_t)n_img * N * 4 + 255) & ~(size_t)255) + (size_t)G * S * C * 4;
 }
@@ -438,10 +505,21 @@ extern "C" int as_cosine_maps(const float* feats, long long feat_img_stride, int
   if (C % 4 || workspace_bytes < as_cosine_maps_workspace(n_img, G, S, N, C)) return AS_ERR_BAD_ARG;
   float* den = (float*)workspace;
   float* phat = (float*)((char*)workspace + (((size_t)n_img * N * 4 + 255) & ~(size_t)255));
-  ms_token_norm<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, den);
   ms_proto_norm<<<G * S, 256, 0, stream>>>(protos, phat, C);
-  ms_sim<<<dim3((N + SIM_TOK - 1) / SIM_TOK, (S + SIM_SG - 1) / SIM_SG, G), SIM_TOK, 0, stream>>>(
-      feats, feat_img_stride, den, grp_img, nullptr, phat, N, C, N, 1, S, 0, clamp0, sim, nullptr, nullptr, nullptr);
+  if (C % 128 == 0 && C <= 1024) {
+    const size_t smem = (size_t)CW_SEEDS * C * 4;
+    static bool attr = false;
+    if (!attr) {
+      AS_CUDA(cudaFuncSetAttribute(cos_warp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SEEDS * 1024 * 4));
+      attr = true;
+    }
+    cos_warp_rows<<<dim3((N + CW_TOK - 1) / CW_TOK, (S + CW_SEEDS - 1) / CW_SEEDS, G), 256, smem, stream>>>(
+        feats, feat_img_stride, grp_img, phat, N, C, S, clamp0, sim);
+  } else {
+    ms_token_norm<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, den);
+    ms_sim<<<dim3((N + SIM_TOK - 1) / SIM_TOK, (S + SIM_SG - 1) / SIM_SG, G), SIM_TOK, 0, stream>>>(
+        feats, feat_img_stride, den, grp_img, nullptr, phat, N, C, N, 1, S, 0, clamp0, sim, nullptr, nullptr, nullptr);
+  }
   AS_LAUNCH_CHECK();
   return 0;
 }
