@@ -960,6 +960,10 @@ int mhsa_variant() {
 // Schedule of the attention forward: 1 = first-generation kernel (two passes over S per tile), 2 = single pass with a window
 // test per chunk, 3 = single pass with the row-sum test, 4 (default) = 3 with a quarter of the exponentials on the FMA pipe
 // (measured at B=8, T=4197, 12 heads: 0.68 / 0.60 / 0.61 / 0.55 ms).  Also: env AS_MHSA_VARIANT.
+// Two further schedules were built, verified against the same tests and dropped because they did not move the time:
+// eight softmax warps per CTA (two threads per query row, verdict / maximum exchanged through a 64-thread named barrier):
+// 0.563 ms, and 64-key tiles with S and P double-buffered in TMEM (the softmax warps never wait for the tensor cores):
+// 0.568 ms.  Neither latency nor warp count is what bounds this kernel.
 extern "C" int as_mhsa_set_variant(int v) {
   if (v < 1 || v > 4) return AS_ERR_BAD_ARG;
   g_mhsa_variant = v;
