@@ -179,6 +179,8 @@ def run_ours(args):
     if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
         os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line the driver parses
     rank, world, local = parallel.env_rank_world()
+    # the host side of a rank is one launching thread: keep torch's CPU pool from oversubscribing the box when 8 ranks share it
+    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 8) // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     parallel.init('nccl', dev)

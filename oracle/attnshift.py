@@ -515,3 +515,112 @@ def attention_shift_image(cams_up, gt_index, pseudo_boxes, vit_feat, gt_points, 
                 semantic_centers_org=(sc[6], sc[7]), corres_gts=sc[8],
                 pseudo_gt_masks=pseudo_masks(fg[-1], pos_mask_thr), inst_fg_feat=f_fg, inst_bg_feat=f_bg,
                 points_a=p_a, points_b=p_b)
+
+
+# --------------------------------------------------------------------------- A15 (second-round aggregation)
+def point_sample(feats, points, **kw):
+    """mmcv.ops.point_sample (mmcv-full 1.3.8, ``mmcv/ops/point_sample.py``; third-party, absent from the reference tree --
+    restated from its published source, PARITY UNPINNED for this one call): bilinear ``grid_sample`` at points given in
+    [0,1] x [0,1] (x, y), ``align_corners=False``.  feats [N,C,H,W]; points [N,P,2] -> [N,C,P], or [N,Hg,Wg,2] -> [N,C,Hg,Wg]."""
+    add_dim = points.dim() == 3
+    if add_dim:
+        points = points.unsqueeze(2)
+    out = F.grid_sample(feats, points * 2.0 - 1.0, align_corners=False, **kw)
+    return out.squeeze(3) if add_dim else out
+
+
+def extract_bg_coords(bg_map, num_groups=3, num_points_per_group=5, hook=None, key=None):
+    """RH:28-49: up to ``num_groups * num_points_per_group`` random non-zero pixels of ``bg_map`` [H,W] (``torch.randperm``
+    on the CPU generator), repeated to the full count, as ``(index + 0.5) / size`` -- in (row, col) order and with the POINT
+    order reversed (the reference's ``.flip(0)`` flips dim 0 of the [P,2] array).  -> [num_groups, P, 2]."""
+    nz = torch.nonzero(bg_map)
+    max_points = num_groups * num_points_per_group
+    if nz.size(0) == 0:
+        idx = torch.ones(max_points, 2, dtype=nz.dtype)
+    else:
+        k = min(max_points, nz.size(0))
+        perm = hook(key, nz.size(0)) if hook is not None else torch.randperm(nz.size(0))
+        idx = nz[perm[:k]]
+        while idx.size(0) < max_points:
+            idx = torch.cat((idx, nz[perm[:max_points - idx.size(0)]]))
+    coords = idx.float() + 0.5
+    coords = (coords / coords.new_tensor(bg_map.shape[:2])).flip(0)
+    return coords.reshape(num_groups, -1, 2)
+
+
+def refined_similarity_input_map(cos_map, feats, bboxes, refine_times=1, tau=0.85, is_select=False):
+    """RH:710-748 ``get_refined_similarity_input_map``: the refinement loop of RH:668-707 started from given maps.
+    cos_map [K,Hp,Wp] (modified in place like the reference), feats [1,C,Hp,Wp] -> (maps [refine_times+1,K,Hp,Wp], centroids)."""
+    cur = cos_map.clone()
+    n_obj = bboxes.shape[0]
+    bmask = box_to_mask(bboxes // PATCH, cos_map.shape[-2:], default=0)
+    outs = []
+
+    def emit(m):
+        if is_select:
+            m[:n_obj] = m[:n_obj] * bmask
+            win = m.argmax(0, keepdim=True).expand_as(m)
+            rows = torch.arange(m.shape[0])
+            outs.append(torch.where(win == rows[:, None, None], m.clone(), torch.zeros_like(m)))
+        else:
+            outs.append(m.clone())
+
+    emit(cos_map)
+    centroid = None
+    for _ in range(refine_times):
+        mx = cur.flatten(1).max(1, keepdim=True)[0].unsqueeze(-1)
+        cur[cur < mx * tau] *= 0
+        w = cur.unsqueeze(1)
+        centroid = (feats * w).sum([2, 3], keepdim=True) / w.sum([2, 3], keepdim=True).clamp(1e-8)
+        cur = F.cosine_similarity(feats, centroid, dim=1)
+        emit(cur)
+    return torch.stack(outs), centroid
+
+
+def update_fg_map_single(map_cos_fg, feats, coords, num_parts, inst_fg_feats, inst_bg_feats, bboxes, img_size, hook=None,
+                         key=None):
+    """RH:2812-2844 ``update_fg_map_single_v3``.  map_cos_fg [n,H,W]; feats [1,C,Hp,Wp]; coords [P,2] part centres (x,y)
+    pixels; num_parts: parts per instance; inst_fg_feats [1,n+1,C]; inst_bg_feats [1,n,C]; bboxes [n,4]; img_size (W,H).
+    -> refined instance maps [n,H,W].  Kept quirks of the reference: the part features enter as the SCALAR mean of all
+    their elements (``torch.mean`` without a dim), and the background supplement is sampled at (row, col) fed as (x, y)."""
+    sc_feat = point_sample(feats, (coords / img_size)[None]).permute(0, 2, 1)
+    split = sc_feat.split(num_parts, dim=1)
+    n = bboxes.shape[0]
+    inst = []
+    for i in range(n):
+        inst.append(torch.mean(split[i]) * 0.5 + inst_fg_feats[:, i] * 0.5 if split[i].shape[0] != 0 else inst_fg_feats[:, i])
+    inst.append(inst_fg_feats[:, -1])
+    inst = torch.cat(inst, dim=0)
+    bg_map = map_cos_fg.sum(0) == 0
+    bg_coords = extract_bg_coords(bg_map, num_groups=1, hook=hook, key=key)
+    bg_supp = point_sample(feats, bg_coords[None], mode='bilinear').mean(-1).permute(0, 2, 1)[0]
+    inst = torch.cat((inst, bg_supp), dim=0)
+    fn = feats / torch.norm(feats, p=2, keepdim=True, dim=1)
+    attn = torch.einsum('nchw, nmc -> nmhw', fn, inst[None] / torch.norm(inst[None], p=2, keepdim=True, dim=2))
+    bg_attn = torch.einsum('nchw, nmc -> nmhw', fn, inst_bg_feats / torch.norm(inst_bg_feats, p=2, keepdim=True, dim=2))
+    attn, _ = refined_similarity_input_map(attn[0], feats, bboxes, 3, is_select=True)
+    size = map_cos_fg.shape[-2:]
+    attn = F.interpolate(attn[-1, :n][None], size, mode='bilinear')[0]
+    bg_attn = F.interpolate(bg_attn, size, mode='bilinear')[0]
+    attn = (1 - bg_attn) * attn
+    attn /= attn.flatten(-2, -1).max(-1, keepdim=True)[0].unsqueeze(-1).clamp(1e-8)
+    return attn.detach().clone()
+
+
+def update_fg_map(map_cos_fg, vit_feat, coords, num_parts, inst_fg_feat, inst_bg_feat, gt_bboxes, pos_mask_thr, hook=None):
+    """RH:2737-2760 ``update_fg_map`` for a batch.  map_cos_fg: list of [n_i,H,W]; vit_feat [B,1+N,C] (cls token first);
+    coords / num_parts / gt_bboxes: per image; inst_fg_feat [n_i+1,C,1,1], inst_bg_feat [n_i,C,1,1] (seed_pseudo_gt outputs).
+    -> (list of refined maps, list of uint8 masks)."""
+    img_size = vit_feat.new_tensor(map_cos_fg[0].shape[-2:][::-1])
+    patch = (img_size.flip(0) // 16).long().tolist()
+    maps, masks = [], []
+    for i in range(vit_feat.shape[0]):
+        feats = vit_feat[[i]][:, 1:].permute(0, 2, 1).unflatten(-1, patch)
+        attn = update_fg_map_single(map_cos_fg[i], feats, coords[i], num_parts[i], inst_fg_feat[i][:, :, 0, 0][None],
+                                    inst_bg_feat[i][:, :, 0, 0][None], gt_bboxes[i], img_size, hook=hook, key=(i, 2, 0))
+        drop = attn.sum(dim=[1, 2]) == 0
+        attn[drop] = map_cos_fg[i][drop]
+        maps.append(attn)
+        masks.append(torch.where(attn > attn.flatten(1).max(1)[0][:, None, None] * pos_mask_thr, torch.ones_like(attn),
+                                 torch.zeros_like(attn)).to(torch.uint8))
+    return maps, masks

@@ -14,7 +14,9 @@ TEST INFRASTRUCTURE.  Mechanism:
   way with stubs for BACKBONES / load_checkpoint / get_root_logger.
 
 ``cc_torch.connected_components_labeling`` is absent from the tree; the loader
-injects the oracle's scipy 8-connectivity stand-in (documented as unpinned).
+injects the oracle's scipy 8-connectivity stand-in (documented as unpinned).  ``mmcv.ops.point_sample`` (only used by
+the second-round aggregation, RH:2737-2844) is injected the same way: a restatement of mmcv-full 1.3.8's published
+``F.grid_sample`` wrapper.
 """
 import ast
 import math
@@ -101,10 +103,10 @@ def load_rh():
     the class methods we need as plain functions taking ``self`` first."""
     if "rh" in _cache:
         return _cache["rh"]
-    from oracle.attnshift import ccl_label  # unpinned cc_torch stand-in
+    from oracle.attnshift import ccl_label, point_sample  # unpinned stand-ins for cc_torch / mmcv.ops.point_sample
     src = open(os.path.join(REF_ROOT, RH_PATH)).read()
     tree = ast.parse(src)
-    ns = dict(torch=torch, nn=nn, F=F, math=math, random=random, np=np, os=os,
+    ns = dict(torch=torch, nn=nn, F=F, math=math, random=random, np=np, os=os, point_sample=point_sample,
               connected_components_labeling=lambda m: torch.from_numpy(
                   ccl_label(m.cpu().numpy())).to(m.device))
     methods = {}

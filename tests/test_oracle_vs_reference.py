@@ -72,3 +72,29 @@ def test_vit_block_bit_exact():
         oy, oa = V.block(x, sd, 'b.', 2)
     assert torch.equal(ry, oy)
     assert torch.equal(ra.mean(1), oa)
+
+
+@pytest.mark.parametrize('hp,c,n_obj,seed', [(20, 48, 3, 9), (28, 64, 3, 11)])
+def test_update_fg_map_bit_exact(hp, c, n_obj, seed):
+    """A15: second-round aggregation (RH:2737-2844) on the outputs of the first round."""
+    rh = ref_loader.load_rh()
+    sc = structured_scene(hp, hp, c, n_obj, seed=seed, noise=0.4)
+    H = hp * 16
+    up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (H, H), mode='bilinear').reshape(7, n_obj, H, H)
+    torch.manual_seed(seed)
+    o = O.attention_shift_image(up, sc['gt_index'], sc['rois'], sc['vit_feat'].clone(), sc['gt_points'], sc['gt_labels'],
+                                mean_shift_times=4)
+    vit = torch.cat((torch.zeros(1, 1, c), sc['vit_feat'].flatten(1).t()[None]), dim=1)          # [1, 1+N, C], cls first
+    coords = torch.cat(o['semantic_centers_split']) if len(o['semantic_centers_split']) else torch.zeros(0, 2)
+    num_parts = [int(s.shape[0]) for s in o['semantic_centers_split']]
+    assert min(num_parts) > 0
+    args = ([o['map_cos_fg']], None, vit, [coords], [num_parts], [o['inst_fg_feat']], [o['inst_bg_feat']], [sc['rois']], 0.6)
+    self_ = SimpleNamespace()
+    self_.update_fg_map_single_v3 = lambda *a, **k: rh.methods.update_fg_map_single_v3(self_, *a, **k)
+    torch.manual_seed(seed + 1)
+    r_maps, r_masks = rh.methods.update_fg_map(self_, *[a.clone() if torch.is_tensor(a) else a for a in args])
+    torch.manual_seed(seed + 1)
+    o_maps, o_masks = O.update_fg_map(args[0], args[2].clone(), args[3], args[4], args[5], args[6], args[7], args[8])
+    assert torch.equal(r_maps[0], o_maps[0])
+    assert (torch.from_numpy(r_masks[0]) == o_masks[0]).all()
+    assert o_maps[0].abs().sum() > 0
