@@ -18,6 +18,7 @@ import ctypes
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from . import lib as _l
 from . import ops
@@ -425,7 +426,7 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
                                         _p(centroid), _p(ws), nb, _sp()), 'as_weighted_centroid')
         cur = cosine_maps(feats, grp.d_img, centroid)
         _l.check(L.as_refine_select(_p(cur), grp.G, grp.S, N, wp, _p(grp.d_first), _p(grp.d_n), _p(rois),
-                                    int(r == refine_times - 1), _p(fg_low), _p(bg_low), _sp()), 'as_refine_select')
+                                    int(r == refine_times - 1), 1, _p(fg_low), _p(bg_low), _sp()), 'as_refine_select')
     # ---- full resolution
     map_fg = torch.empty(n_tot, H, W, device=dev, dtype=torch.float32)
     map_bg = torch.empty(n_tot, H, W, device=dev, dtype=torch.float32) if want_bg else None
@@ -583,6 +584,91 @@ def assemble_parts(parts, n_per_img, gt_labels, hp, wp, num_max_keep=50):
         o += n
         c0 += cnt
     return out
+
+
+# --------------------------------------------------------------------------------------------------- A15
+def update_fg_maps(map_cos_fg, feats, coords, num_parts, inst_fg_feat, inst_bg_feat, rois, n_per_img, hp, wp, rng,
+                   pos_mask_thr=0.6, refine_times=3, tau=0.85):
+    """Second-round aggregation, RH:2737-2844 (``update_fg_map`` + ``update_fg_map_single_v3`` + ``extract_bg_coords`` +
+    ``get_refined_similarity_input_map``) for the whole batch.
+    map_cos_fg [n_tot,H,W] first-round maps; feats [n_img,N,C] token-major; coords: per image [P_i,2] part centres (x, y)
+    pixels; num_parts: per image, parts per instance; inst_fg_feat / inst_bg_feat: per image [n_i+1,C,1,1] / [n_i,C,1,1]
+    (``seed_pseudo_gt`` outputs); rois [n_tot,4].  -> (maps [n_tot,H,W] fp32, masks [n_tot,H,W] uint8), instances flat.
+    The prototypes are a few dozen vectors assembled with torch glue (the reference samples them with mmcv's point_sample =
+    ``F.grid_sample``, kept as is, quirks included); the affinity / refinement / fusion passes are the first round's kernels."""
+    L = _l.load()
+    dev = feats.device
+    n_img, N, C = feats.shape
+    n_tot, H, W = map_cos_fg.shape
+    plan = _seed_plan(n_per_img, dev, 0.2, 0.1)
+    grp = plan['grp']
+    S = max(n_per_img) + 2
+    obj_img = instance_image_index(n_per_img, dev)
+    fmap = feats.view(n_img, hp, wp, C).permute(0, 3, 1, 2)             # [n_img,C,hp,wp] view for grid_sample
+    img_size = torch.tensor([float(W), float(H)], device=dev)
+    # background supplement: 5 random pixels where no first-round map responds (RH:2826-2829)
+    resp = torch.zeros(n_img, H, W, device=dev, dtype=map_cos_fg.dtype).index_add_(0, obj_img.long(), map_cos_fg)
+    nz = torch.nonzero(resp == 0)                                         # host sync: [K,3] (image, row, col), row-major
+    per_img = torch.bincount(nz[:, 0], minlength=n_img).tolist()
+    starts = np.concatenate(([0], np.cumsum(per_img)))
+    pick = []
+    for g in range(n_img):
+        cnt = per_img[g]
+        if cnt == 0:
+            pick.append(None)
+            continue
+        head = rng.randperm_head((g, 2, 0), cnt, 5).tolist()
+        sel = list(head)
+        while len(sel) < 5:
+            sel += head[:5 - len(sel)]
+        pick.append([int(starts[g]) + k for k in sel])
+    flat = [k for p_ in pick if p_ is not None for k in p_]
+    d_pick, = _upload_i32([flat], dev)
+    chosen = nz.index_select(0, d_pick.long())[:, 1:].float() if flat else nz[:0, 1:].float()
+    protos = torch.zeros(grp.G, S, C, device=dev, dtype=torch.float32)
+    bg_protos = torch.empty(n_tot, 1, C, device=dev, dtype=torch.float32)
+    o = c0 = 0
+    for g, n in enumerate(n_per_img):
+        fg_f = inst_fg_feat[g].reshape(n + 1, C)
+        bg_protos[o:o + n, 0] = inst_bg_feat[g].reshape(n, C)
+        pts = (coords[g].to(dev).float() / img_size)[None, :, None, :]     # [1,P,1,2] in [0,1]: mmcv point_sample
+        sc = F.grid_sample(fmap[g:g + 1], pts * 2.0 - 1.0, align_corners=False)[0, :, :, 0].t()      # [P,C]
+        for j, s_ in enumerate(sc.split(list(num_parts[g]), dim=0)):
+            protos[g, j] = torch.mean(s_) * 0.5 + fg_f[j] * 0.5             # scalar mean of ALL elements, as the reference
+        protos[g, n] = fg_f[n]
+        if pick[g] is None:
+            idx = torch.ones(5, 2, device=dev)
+        else:
+            idx = chosen[c0:c0 + 5]
+            c0 += 5
+        bc = ((idx + 0.5) / torch.tensor([float(H), float(W)], device=dev)).flip(0)[None, None]        # [1,1,5,2], (row, col) fed as (x, y)
+        protos[g, n + 1] = F.grid_sample(fmap[g:g + 1], bc * 2.0 - 1.0, mode='bilinear', align_corners=False)[0, :, 0].mean(-1)
+        o += n
+    # affinity, refinement loop (threshold -> weighted centroid -> affinity -> box mask / winner-take-all), fusion
+    bg_low = cosine_maps(feats, obj_img, bg_protos).reshape(n_tot, N)
+    cur = cosine_maps(feats, grp.d_img, protos)
+    GS = grp.G * S
+    wsum = torch.empty(GS, device=dev, dtype=torch.float32)
+    nb = L.as_weighted_centroid_workspace(grp.G, S, N, C)
+    ws = _ws(nb, dev)
+    fg_low = torch.empty(n_tot, N, device=dev, dtype=torch.float32)
+    for r in range(refine_times):
+        _l.check(L.as_refine_threshold(_p(cur), GS, N, float(tau), _p(wsum), _sp()), 'as_refine_threshold')
+        centroid = torch.empty(grp.G, S, C, device=dev, dtype=torch.float32)
+        _l.check(L.as_weighted_centroid(_p(feats), feats.stride(0), _p(grp.d_img), _p(cur), _p(wsum), grp.G, S, N, C,
+                                        _p(centroid), _p(ws), nb, _sp()), 'as_weighted_centroid')
+        cur = cosine_maps(feats, grp.d_img, centroid)
+        _l.check(L.as_refine_select(_p(cur), grp.G, S, N, wp, _p(grp.d_first), _p(grp.d_n), _p(rois),
+                                    int(r == refine_times - 1), 2, _p(fg_low), None, _sp()), 'as_refine_select')
+    maps = torch.empty(n_tot, H, W, device=dev, dtype=torch.float32)
+    mask = torch.empty(n_tot, H, W, device=dev, dtype=torch.uint8)
+    stats = torch.empty(n_tot * 3, device=dev, dtype=torch.int32)
+    _l.check(L.as_fuse_instance_maps(_p(fg_low), _p(bg_low), n_tot, hp, wp, float(pos_mask_thr), _p(maps), None, _p(mask),
+                                     _p(stats), _sp()), 'as_fuse_instance_maps')
+    # an instance whose refined map vanished keeps its first-round map (RH:2754-2756)
+    drop = (maps.flatten(1).sum(1) == 0)[:, None, None]
+    old_mask = (map_cos_fg > map_cos_fg.flatten(1).max(1)[0][:, None, None] * pos_mask_thr).to(torch.uint8)
+    return torch.where(drop, map_cos_fg, maps), torch.where(drop, old_mask, mask)
 
 
 def cam_minmax(lows, hp, wp):

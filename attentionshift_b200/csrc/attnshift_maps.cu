@@ -223,10 +223,12 @@ __global__ void weighted_sum_finish(const float* __restrict__ part, const float*
     out[(size_t)row * C + c] = v / den;
   }
 }
-// per image group g (rows: [0,n) fg instances, n = supp, (n, 2n] bg instances):
-//   fg rows *= box mask (in place, RH:699); optionally emit fg (winner-take-all over rows 0..n, RH:700-703) and bg.
+// per image group g (rows: [0,n) fg instances, then n_extra rows that also compete -- the bg supplement(s) -- then, in the
+// first-round layout, n bg instances):
+//   fg rows *= box mask (in place, RH:699 / RH:740); optionally emit fg (winner-take-all over rows 0..n+n_extra-1,
+//   RH:700-703 / RH:741-743) and bg (rows n+1..2n; first round only, bg_out may be null).
 __global__ void refine_select(float* __restrict__ cur, int S, int N, int wp, const int* __restrict__ grp_first,
-                              const int* __restrict__ grp_nobj, const float* __restrict__ rois, int emit,
+                              const int* __restrict__ grp_nobj, const float* __restrict__ rois, int emit, int n_extra,
                               float* __restrict__ fg_out, float* __restrict__ bg_out) {
   const int g = blockIdx.y;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,7 +238,7 @@ __global__ void refine_select(float* __restrict__ cur, int S, int N, int wp, con
   const int r = n / wp, cidx = n - r * wp;
   float best = -FLT_MAX;
   int bi = 0;
-  for (int j = 0; j <= nobj; ++j) {
+  for (int j = 0; j < nobj + n_extra; ++j) {
     float v = cg[(size_t)j * N + n];
     if (j < nobj) {
       const float* roi = rois + 4 * (o0 + j);
@@ -251,7 +253,7 @@ __global__ void refine_select(float* __restrict__ cur, int S, int N, int wp, con
   if (emit) {
     for (int j = 0; j < nobj; ++j) {
       fg_out[(size_t)(o0 + j) * N + n] = (bi == j) ? cg[(size_t)j * N + n] : 0.f;
-      bg_out[(size_t)(o0 + j) * N + n] = cg[(size_t)(nobj + 1 + j) * N + n];
+      if (bg_out) bg_out[(size_t)(o0 + j) * N + n] = cg[(size_t)(nobj + 1 + j) * N + n];
     }
   }
 }
@@ -512,9 +514,11 @@ extern "C" int as_weighted_centroid(const float* feats, long long feat_img_strid
   return 0;
 }
 extern "C" int as_refine_select(float* cur, int G, int S, int N, int wp, const int* grp_first, const int* grp_nobj,
-                                const float* rois, int emit, float* fg_out, float* bg_out, cudaStream_t stream) {
+                                const float* rois, int emit, int n_extra, float* fg_out, float* bg_out, cudaStream_t stream) {
   if (G <= 0) return 0;
-  refine_select<<<dim3((N + 255) / 256, G), 256, 0, stream>>>(cur, S, N, wp, grp_first, grp_nobj, rois, emit, fg_out, bg_out);
+  if (n_extra < 0 || (emit && !fg_out)) return AS_ERR_BAD_ARG;
+  refine_select<<<dim3((N + 255) / 256, G), 256, 0, stream>>>(cur, S, N, wp, grp_first, grp_nobj, rois, emit, n_extra, fg_out,
+                                                              bg_out);
   AS_LAUNCH_CHECK();
   return 0;
 }

@@ -61,6 +61,27 @@ class AttnShiftRoIHead(nn.Module):
             out.append(torch.as_tensor(r)[order].long())
         return out
 
+    @torch.no_grad()
+    def update_fg_map(self, map_cos_fg, map_cos_bg, vit_feat, semantic_centers_coords, obj_num_parts, inst_fg_feat, inst_bg_feat,
+                      gt_bboxes, pos_mask_thr):
+        """RH:2737-2760, same signature and return value: the second-round aggregation of the part centres into refined
+        instance maps (``update_fg_map_single_v3``) and their pseudo masks.  map_cos_fg: list of [n_i,H,W]; vit_feat
+        [B,1+N,C] (cls token first); semantic_centers_coords: list of [P_i,2]; obj_num_parts: list of lists; inst_fg_feat /
+        inst_bg_feat: the ``seed_pseudo_gt`` outputs; gt_bboxes: list of [n_i,4].
+        -> (list of [n_i,H,W] maps on the device, list of uint8 numpy masks)."""
+        n_per_img = [int(m.shape[0]) for m in map_cos_fg]
+        H, W = map_cos_fg[0].shape[-2:]
+        hp, wp = H // 16, W // 16
+        feats = AS.token_major(vit_feat[:, 1:])
+        dev = feats.device
+        maps, masks = AS.update_fg_maps(torch.cat(list(map_cos_fg)).contiguous(), feats, semantic_centers_coords, obj_num_parts,
+                                        inst_fg_feat, inst_bg_feat, torch.cat([b.reshape(-1, 4).float() for b in gt_bboxes]).to(dev).contiguous(),
+                                        n_per_img, hp, wp, self.rng, pos_mask_thr=pos_mask_thr)
+        m_host = torch.empty(masks.shape, dtype=torch.uint8, pin_memory=True)
+        m_host.copy_(masks, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return list(maps.split(n_per_img, dim=0)), [m.numpy() for m in m_host.split(n_per_img, dim=0)]
+
     def seed_pseudo_gt(self, x, img_metas, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore=None, gt_masks=None,
                        vit_feat=None, img=None, point_init=None, point_cls=None, point_reg=None, imgs_whwh=None,
                        attns=None, gt_points=None, gt_points_labels=None, roi_feature_map=None, return_mask=False,

@@ -54,7 +54,7 @@ SIGNATURES = {
     'as_refine_threshold': (_i, [_vp, _i, _i, _f, _vp, _vp]),
     'as_weighted_centroid_workspace': (_sz, [_i, _i, _i, _i]),
     'as_weighted_centroid': (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    'as_refine_select': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    'as_refine_select': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'as_fuse_instance_maps': (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     'as_mask_candidates_workspace': (_sz, [_i, _i, _i]),
     'as_mask_candidates': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -123,8 +123,11 @@ size_t as_weighted_centroid_workspace(int G, int S, int N, int C);
 int as_weighted_centroid(const float* feats, long long feat_img_stride, const int* grp_img, const float* w,
                          const float* wsum, int G, int S, int N, int C, float* out, void* workspace,
                          size_t workspace_bytes, as_stream_t stream);
+/* Rows of group g: [0,n) instances (multiplied in place by their patch-grid box mask), then n_extra further rows that take
+ * part in the winner-take-all (first round, RH:668-707: 1 = the image-level bg supplement, followed by n bg rows copied to
+ * bg_out; second round, RH:710-748 / RH:2812-2844: 2 = fg supplement + sampled bg supplement, bg_out = NULL). */
 int as_refine_select(float* cur, int G, int S, int N, int wp, const int* grp_first, const int* grp_nobj,
-                     const float* rois, int emit, float* fg_out, float* bg_out, as_stream_t stream);
+                     const float* rois, int emit, int n_extra, float* fg_out, float* bg_out, as_stream_t stream);
 /* RH:1010-1019 + RH:2356: full-resolution fg / bg maps and uint8 pseudo masks from the low-resolution affinities. */
 int as_fuse_instance_maps(const float* fg_low, const float* bg_low, int n_tot, int hp, int wp, float mask_thr,
                           float* map_fg, float* map_bg, unsigned char* mask, void* stats_scratch, as_stream_t stream);

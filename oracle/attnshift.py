@@ -539,7 +539,9 @@ def extract_bg_coords(bg_map, num_groups=3, num_points_per_group=5, hook=None, k
         idx = torch.ones(max_points, 2, dtype=nz.dtype)
     else:
         k = min(max_points, nz.size(0))
-        perm = hook(key, nz.size(0)) if hook is not None else torch.randperm(nz.size(0))
+        if hook is not None:
+            hook(key)                       # test hook: re-seed the CPU generator per (image, stage, instance) key
+        perm = torch.randperm(nz.size(0))
         idx = nz[perm[:k]]
         while idx.size(0) < max_points:
             idx = torch.cat((idx, nz[perm[:max_points - idx.size(0)]]))

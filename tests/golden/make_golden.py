@@ -64,6 +64,31 @@ def attnshift_case(hp, c, n_obj, scene_seed, rng_seed, noise, n_shift, keep_maps
     return g
 
 
+def update_fg_case(hp, c, n_obj, scene_seed, rng_seed):
+    """A15 (RH:2737-2844): the reference's second-round aggregation on the oracle-produced first round (which the other
+    goldens pin against the reference)."""
+    from oracle import attnshift as O
+    rh = ref_loader.load_rh()
+    sc = structured_scene(hp, hp, c, n_obj, seed=scene_seed, noise=0.4)
+    H = hp * 16
+    up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (H, H), mode='bilinear').reshape(7, n_obj, H, H)
+    torch.manual_seed(scene_seed)
+    o = O.attention_shift_image(up, sc['gt_index'], sc['rois'], sc['vit_feat'].clone(), sc['gt_points'], sc['gt_labels'],
+                                mean_shift_times=4)
+    vit = torch.cat((torch.zeros(1, 1, c), sc['vit_feat'].flatten(1).t()[None]), dim=1)
+    coords = torch.cat(o['semantic_centers_split'])
+    num_parts = [int(x.shape[0]) for x in o['semantic_centers_split']]
+    assert min(num_parts) > 0
+    self_ = SimpleNamespace()
+    self_.update_fg_map_single_v3 = lambda *a, **k: rh.methods.update_fg_map_single_v3(self_, *a, **k)
+    torch.manual_seed(rng_seed)
+    maps, masks = rh.methods.update_fg_map(self_, [o['map_cos_fg'].clone()], None, vit.clone(), [coords], [num_parts],
+                                           [o['inst_fg_feat']], [o['inst_bg_feat']], [sc['rois']], 0.6)
+    return dict(meta=dict(hp=hp, c=c, n_obj=n_obj, scene_seed=scene_seed, rng_seed=rng_seed, torch=str(torch.__version__)),
+                maps=maps[0].half(),      # fp16 keeps the fixture small; far finer than the tests' 1e-3
+                masks_packed=torch.from_numpy(__import__('numpy').packbits(masks[0])))
+
+
 def rollout_case(t, layers, b, seed):
     rh = ref_loader.load_rh()
     gen = torch.Generator().manual_seed(seed)
@@ -97,6 +122,7 @@ if __name__ == '__main__':
                os.path.join(OUT, 'attnshift_224_c32.pt'))
     torch.save(attnshift_case(28, 64, 3, scene_seed=3, rng_seed=7, noise=0.4, n_shift=10, keep_maps=False),
                os.path.join(OUT, 'attnshift_448_c64.pt'))
+    torch.save(update_fg_case(20, 48, 3, scene_seed=9, rng_seed=10), os.path.join(OUT, 'update_fg_320_c48.pt'))
     torch.save(rollout_case(t=61, layers=7, b=2, seed=1), os.path.join(OUT, 'rollout_t61.pt'))
     torch.save(vit_case(embed=128, heads=2, depth=2, img=64, n_pt=12, seed=0), os.path.join(OUT, 'vit_e128_d2.pt'))
     for f in sorted(os.listdir(OUT)):

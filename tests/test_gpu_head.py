@@ -65,3 +65,41 @@ def test_seed_pseudo_gt_vs_oracle():
             assert _iou(torch.from_numpy(out['pseudo_gt_masks'][i][j]), o['pseudo_gt_masks'][j]) >= 0.999
         assert out['num_parts'][i] == o['num_parts']
         torch.testing.assert_close(out['semantic_centers_org'][0][i].cpu(), o['semantic_centers_org'][0], rtol=0, atol=0)
+
+
+def test_update_fg_map_vs_oracle():
+    """A15 (RH:2737-2844): second-round aggregation on the device against the oracle, two images in one batch; the first
+    round (maps, instance features, part centres) comes from the oracle so that only this stage is under test."""
+    from attentionshift_b200 import attention_shift as AS
+    from attentionshift_b200.registry import build_head
+    from attentionshift_b200.synthetic import structured_scene
+    hp, c, n = 20, 48, 3
+    H = hp * 16
+    rng = AS.KeyedRng(21)
+    head = build_head(dict(type='AttnShiftRoIHead', bbox_head=dict(cam_layer=7), rng=rng))
+    first, vit = [], []
+    for seed in (9, 17):
+        sc = structured_scene(hp, hp, c, n, seed=seed, noise=0.4)
+        up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (H, H), mode='bilinear').reshape(7, n, H, H)
+        torch.manual_seed(seed)
+        o = O.attention_shift_image(up, sc['gt_index'], sc['rois'], sc['vit_feat'].clone(), sc['gt_points'], sc['gt_labels'],
+                                    mean_shift_times=4)
+        assert min(int(s.shape[0]) for s in o['semantic_centers_split']) > 0
+        first.append((sc, o))
+        vit.append(torch.cat((torch.zeros(1, c), sc['vit_feat'].flatten(1).t()), dim=0))
+    vit = torch.stack(vit)                                                              # [2, 1+N, C]
+    fg = [o['map_cos_fg'] for _, o in first]
+    coords = [torch.cat(o['semantic_centers_split']) for _, o in first]
+    parts = [[int(s.shape[0]) for s in o['semantic_centers_split']] for _, o in first]
+    f_fg = [o['inst_fg_feat'] for _, o in first]
+    f_bg = [o['inst_bg_feat'] for _, o in first]
+    boxes = [sc['rois'] for sc, _ in first]
+    r_maps, r_masks = O.update_fg_map([m.clone() for m in fg], vit, coords, parts, f_fg, f_bg, boxes, 0.6,
+                                      hook=lambda key: torch.manual_seed(rng.seed_for(key)))
+    maps, masks = head.update_fg_map([m.to(DEV) for m in fg], None, vit.to(DEV), [x.to(DEV) for x in coords], parts,
+                                     [x.to(DEV) for x in f_fg], [x.to(DEV) for x in f_bg], [b.to(DEV) for b in boxes], 0.6)
+    for i in range(2):
+        torch.testing.assert_close(maps[i].cpu(), r_maps[i], rtol=1e-3, atol=1e-4)      # north_star fp32 tolerance
+        assert masks[i].dtype.name == 'uint8' and masks[i].shape == (n, H, H)
+        for j in range(n):
+            assert _iou(torch.from_numpy(masks[i][j]), r_masks[i][j]) >= 0.999

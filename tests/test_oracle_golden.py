@@ -98,3 +98,26 @@ def test_ccl_connectivity_assumption():
     lab = O.ccl_label(a)
     assert lab[0, 0] == lab[1, 1] != 0
     assert lab[3, 0] not in (0, lab[0, 0])
+
+
+def test_update_fg_map(golden_dir):
+    """A15 second-round aggregation (RH:2737-2844) against the reference's output (maps stored as fp16)."""
+    g = torch.load(os.path.join(golden_dir, 'update_fg_320_c48.pt'))
+    m = g['meta']
+    hp, c, n = m['hp'], m['c'], m['n_obj']
+    sc = structured_scene(hp, hp, c, n, seed=m['scene_seed'], noise=0.4)
+    H = hp * 16
+    up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (H, H), mode='bilinear').reshape(7, n, H, H)
+    torch.manual_seed(m['scene_seed'])
+    o = O.attention_shift_image(up, sc['gt_index'], sc['rois'], sc['vit_feat'].clone(), sc['gt_points'], sc['gt_labels'],
+                                mean_shift_times=4)
+    vit = torch.cat((torch.zeros(1, 1, c), sc['vit_feat'].flatten(1).t()[None]), dim=1)
+    coords = torch.cat(o['semantic_centers_split'])
+    num_parts = [int(x.shape[0]) for x in o['semantic_centers_split']]
+    torch.manual_seed(m['rng_seed'])
+    maps, masks = O.update_fg_map([o['map_cos_fg'].clone()], vit, [coords], [num_parts], [o['inst_fg_feat']],
+                                  [o['inst_bg_feat']], [sc['rois']], 0.6)
+    torch.testing.assert_close(maps[0], g['maps'].float(), rtol=2e-3, atol=1e-3)
+    packed = torch.from_numpy(np.packbits(masks[0].numpy()))
+    # the masks threshold the maps at 0.6 x max: bit-equal with the same torch build
+    assert (packed != g['masks_packed']).float().mean().item() < 1e-3
