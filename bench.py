@@ -279,7 +279,7 @@ def run_ours(args):
                 traffic = None
         if att.get('n'):
             ach = flops_attn / (att['ms'] / att['n'] * 1e-3) / 1e12
-            roof = dict(kernel='mhsa_fwd_kernel (tcgen05 flash attention, one launch = one layer x batch)', bound='tensor',
+            roof = dict(kernel='mhsa_fwd2_kernel (tcgen05 flash attention, one launch = one layer x batch)', bound='tensor',
                         achieved=round(ach, 1), peak=pk['tf_sus'], unit='TFLOP/s', frac=round(ach / pk['tf_sus'], 4),
                         traffic=traffic, peak_source=pk['src'] + ' sustained bf16 GEMM', share_of_step=round(att['ms'] / ms_dev, 3))
         ms_name = next((k for k in ('as_mean_shift_fused', 'as_mean_shift_tc', 'as_mean_shift') if fam.get(k, {}).get('n')), 'as_mean_shift')
@@ -291,8 +291,15 @@ def run_ours(args):
             ach2 = b_alg / (msf['ms'] / msf['n'] * 1e-3) / 1e9
             what = {'as_mean_shift_fused': 'one persistent cooperative kernel + the token split kernel',
                     'as_mean_shift_tc': '~50 launches', 'as_mean_shift': 'fp32 CUDA-core kernels'}[ms_name]
+            traffic2 = None
+            t2path = os.path.join(ROOT, 'profiles', 'ncu_msfused_traffic.json')      # dram bytes / launch from the committed ncu capture
+            if ms_name == 'as_mean_shift_fused' and os.path.exists(t2path) and not args.small:
+                try:
+                    traffic2 = json.load(open(t2path)).get('dram_bytes_per_launch')
+                except Exception:
+                    traffic2 = None
             roof2 = dict(kernel='%s (whole on-device attention-shift loop, all images of the batch; %s)' % (ms_name, what), bound='hbm', achieved=round(ach2, 1),
-                         peak=pk['hbm'], unit='GB/s', frac=round(ach2 / pk['hbm'], 4), traffic=None, peak_source=pk['src'])
+                         peak=pk['hbm'], unit='GB/s', frac=round(ach2 / pk['hbm'], 4), traffic=traffic2, peak_source=pk['src'])
         line = dict(metric='images/sec at 1024^2 bs8 ViT-B attn-shift', value=round(world * B / (ms_dev * 1e-3), 2), unit='images/s',
                     n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=round(ms_dev, 3), higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f16 operands / f32 accumulate (ViT GEMMs + attention), f32 (attention shift)',
