@@ -105,18 +105,82 @@ def _f32(x, dev):
     return torch.as_tensor(x, dtype=torch.float32).to(dev, non_blocking=True)
 
 
+class _PinnedRing:
+    """A fixed arena of pinned host memory handed out as a ring: the small host<->device transfers of a step (index
+    uploads, candidate counts) never call cudaHostAlloc again after start-up -- a pinned allocation costs milliseconds and
+    showed up as occasional 50 ms steps when torch's caching host allocator had to grow.  A region is reused only after
+    the event recorded behind its transfer has completed (normally hundreds of steps earlier)."""
+
+    def __init__(self, nbytes=8 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        self.size = nbytes
+        self.head = 0
+        self.inflight = []          # (start, end, event), in allocation order
+
+    def take(self, nbytes):
+        """-> (uint8 view of ``nbytes`` pinned bytes, token for ``done``)."""
+        nbytes = max((int(nbytes) + 255) & ~255, 256)
+        if nbytes > self.size:
+            return self._fresh(nbytes), None
+        for _ in range(4):
+            if self.head + nbytes > self.size:
+                self.head = 0
+            start, end = self.head, self.head + nbytes
+            busy = [e for e in self.inflight if e[0] < end and e[1] > start and e[2] is None]
+            if busy:                                      # still being filled / read by the host: step over it
+                self.head = max(e[1] for e in busy)
+                continue
+            keep = []
+            for ent in self.inflight:
+                if ent[0] < end and ent[1] > start:       # the ring has come round: its transfer must have completed
+                    ent[2].synchronize()
+                else:
+                    keep.append(ent)
+            self.inflight = keep
+            self.head = end
+            token = [start, end, None]
+            self.inflight.append(token)
+            return self.buf[start:end], token
+        return self._fresh(nbytes), None
+
+    @staticmethod
+    def _fresh(nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+    def done(self, token):
+        """The host is finished with the region and the transfer that uses it has been enqueued on the current stream."""
+        if token is not None:
+            token[2] = torch.cuda.Event()
+            token[2].record()
+
+
+_RINGS = {}
+
+
+def _ring(dev):
+    key = str(dev)
+    r = _RINGS.get(key)
+    if r is None:
+        r = _RINGS[key] = _PinnedRing()
+    return r
+
+
 def _upload_i32(arrays, dev):
     """Several small host integer arrays -> the device in ONE pinned, asynchronous copy.  Returns int32 device views (in
     order, shaped like the inputs).  Pageable uploads stall the host for a driver round trip each; this path has dozens."""
     arrays = [np.ascontiguousarray(a, dtype=np.int32) for a in arrays]
     sizes = [a.size for a in arrays]
-    host = torch.empty(max(sum(sizes), 1), dtype=torch.int32, pin_memory=True)
+    total = max(sum(sizes), 1)
+    ring = _ring(dev)
+    raw, token = ring.take(total * 4)
+    host = raw[:total * 4].view(torch.int32)
     hv = host.numpy()
     o = 0
     for a, n in zip(arrays, sizes):
         hv[o:o + n] = a.reshape(-1)
         o += n
     d = host.to(dev, non_blocking=True)
+    ring.done(token)
     out, o = [], 0
     for a, n in zip(arrays, sizes):
         out.append(d[o:o + n].view(a.shape))
@@ -140,13 +204,20 @@ class _Pending:
     """Device -> pinned-host copy enqueued now, awaited later: the host keeps launching kernels while the counts travel."""
 
     def __init__(self, t):
-        self.host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        ring = _ring(t.device)
+        raw, token = ring.take(t.numel() * t.element_size())
+        self.host = raw[:t.numel() * t.element_size()].view(t.dtype).view(t.shape)
         self.host.copy_(t, non_blocking=True)
+        self.ring, self.token = ring, token
         self.ev = torch.cuda.Event()
         self.ev.record()
 
     def get(self):
+        """Host tensor (a view of the pinned ring: read it before the ring comes round, i.e. right away)."""
         self.ev.synchronize()
+        if self.token is not None:
+            self.ring.done(self.token)
+            self.token = None
         return self.host
 
 

@@ -122,6 +122,120 @@ __global__ void rollout_first_ld(const float* __restrict__ A, int ld, const floa
   out[b * out_bstride + (size_t)r * ldo + n] = v;
 }
 
+// ------------------------------------------------------------------ fused split-fp16 slab GEMM on tcgen05
+// out[b, r, n] += alpha * sum_k (Ahi + Alo)[b, r, k] * (Bhi + Blo)[b, n, k]   (the lo.lo term is below fp32 resolution)
+// One CTA = one image x 64 output columns, all 128 slab rows, the whole K range: the T x T operand (570 MB per layer as a
+// hi / lo pair) is read from HBM exactly ONCE -- three separate GEMM launches read its hi half twice and its lo half once.
+constexpr int RT_BN = 64, RT_BK = 64, RT_STAGES = 4;
+constexpr int RT_A = 128 * RT_BK * 2, RT_B = RT_BN * RT_BK * 2;            // 16 KB, 8 KB
+constexpr int RT_STAGE = 2 * RT_A + 2 * RT_B;                             // 48 KB: A hi, A lo, B hi, B lo
+constexpr int RT_SMEM = RT_STAGES * RT_STAGE + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+rollout_mma_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, int kblocks,
+                   int n_rows, int ldo, size_t out_bstride, float alpha, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RT_STAGES * RT_STAGE);
+  uint64_t* empty = full + RT_STAGES;
+  uint64_t* acc_full = empty + RT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * RT_BN, b = blockIdx.y;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_ahi); tma_prefetch_desc(&tm_alo); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
+    for (int i = 0; i < RT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int st = kb % RT_STAGES;
+        mbar_wait(&empty[st], ((kb / RT_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], RT_STAGE);
+        uint8_t* d = smem + st * RT_STAGE;
+        tma_load_3d(d, &tm_ahi, &full[st], kb * RT_BK, 0, b);
+        tma_load_3d(d + RT_A, &tm_alo, &full[st], kb * RT_BK, 0, b);
+        tma_load_3d(d + 2 * RT_A, &tm_bhi, &full[st], kb * RT_BK, n0, b);
+        tma_load_3d(d + 2 * RT_A + RT_B, &tm_blo, &full[st], kb * RT_BK, n0, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(0, 128, RT_BN);
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int st = kb % RT_STAGES;
+      mbar_wait(&full[st], (kb / RT_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + st * RT_STAGE), a_lo = a_hi + RT_A, b_hi = a_hi + 2 * RT_A, b_lo = b_hi + RT_B;
+#pragma unroll
+        for (int k = 0; k < RT_BK / 16; ++k) {
+          mma_f16_ss(tmem, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, (kb | k) != 0);
+          mma_f16_ss(tmem, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1);
+          mma_f16_ss(tmem, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1);
+        }
+        tc_commit(&empty[st]);
+        if (kb == kblocks - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3, r = quad * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < RT_BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      tc_wait_ld();
+      if (r < n_rows) {
+        float4* o4 = reinterpret_cast<float4*>(out + b * out_bstride + (size_t)r * ldo + n0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o = o4[i];                                   // the identity term R' written by rollout_scale_split
+          o.x = fmaf(__uint_as_float(v[4 * i]), alpha, o.x); o.y = fmaf(__uint_as_float(v[4 * i + 1]), alpha, o.y);
+          o.z = fmaf(__uint_as_float(v[4 * i + 2]), alpha, o.z); o.w = fmaf(__uint_as_float(v[4 * i + 3]), alpha, o.w);
+          o4[i] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem);
+}
+
+int rollout_mma(const __half* a_hi, const __half* a_lo, const void* b_hi, const void* b_lo, float* out, int B, int n_rows,
+                int ldt, size_t out_bstride, float alpha, cudaStream_t stream) {
+  CUtensorMap tm[4];
+  uint64_t da[3] = {(uint64_t)ldt, 128, (uint64_t)B}, sa[2] = {(uint64_t)ldt * 2, (uint64_t)128 * ldt * 2};
+  uint32_t ba[3] = {RT_BK, 128, 1};
+  uint64_t db[3] = {(uint64_t)ldt, (uint64_t)ldt, (uint64_t)B}, sb[2] = {(uint64_t)ldt * 2, (uint64_t)ldt * ldt * 2};
+  uint32_t bb[3] = {RT_BK, RT_BN, 1};
+  int r = as_encode_tmap(&tm[0], a_hi, 2, 3, da, sa, ba);
+  if (!r) r = as_encode_tmap(&tm[1], a_lo, 2, 3, da, sa, ba);
+  if (!r) r = as_encode_tmap(&tm[2], b_hi, 2, 3, db, sb, bb);
+  if (!r) r = as_encode_tmap(&tm[3], b_lo, 2, 3, db, sb, bb);
+  if (r) return r;
+  static bool attr = false;
+  if (!attr) {
+    AS_CUDA(cudaFuncSetAttribute(rollout_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
+    attr = true;
+  }
+  rollout_mma_kernel<<<dim3(ldt / RT_BN, B), 192, RT_SMEM, stream>>>(tm[0], tm[1], tm[2], tm[3], ldt / RT_BK, n_rows, ldt,
+                                                                     out_bstride, alpha, out);
+  AS_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M,
@@ -156,11 +270,8 @@ extern "C" int as_rollout_rows_tc(const float* const* attn, const void* const* t
     } else {
       rollout_scale_split<<<dim3((ldt + 255) / 256, 128, B), 256, 0, stream>>>(out + (size_t)(i - 1) * n_rows * ldt, bstride, ldt, rs, T,
                                                                              n_rows, ldt, r_scale, hi, lo, dst, bstride, ldt);
-      int r = as_bgemm_f16_f32(hi, t_hi[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
-      if (r) return r;
-      r = as_bgemm_f16_f32(hi, t_lo[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
-      if (r) return r;
-      r = as_bgemm_f16_f32(lo, t_hi[l], dst, dst, B, n_rows, ldt, ldt, 128, ldt, ldt, (long long)bstride, alpha, stream);
+      // hi.hi + hi.lo + lo.hi in ONE pass over the T x T operand (three GEMM launches would read its hi half twice)
+      const int r = rollout_mma(hi, lo, t_hi[l], t_lo[l], dst, B, n_rows, ldt, bstride, alpha, stream);
       if (r) return r;
     }
   }

@@ -44,6 +44,19 @@ class AttnShiftRoIHead(nn.Module):
         self.rng = rng if rng is not None else AS.KeyedRng(0)
         self.with_mil = mil_head is not None or mil_fn is not None
         self.with_deform_sup = False
+        self._mask_bufs = {}
+
+    def _mask_buffer(self, shape):
+        """Pinned landing buffer for the uint8 masks (RH:2358 hand-off).  Two buffers per shape alternate, so the numpy views
+        handed out by one call stay valid until the call after the next; no cudaHostAlloc in the steady state."""
+        key = tuple(shape)
+        ent = self._mask_bufs.get(key)
+        if ent is None:
+            if len(self._mask_bufs) > 8:
+                self._mask_bufs.clear()
+            ent = self._mask_bufs[key] = [[torch.empty(key, dtype=torch.uint8, pin_memory=True) for _ in range(2)], 0]
+        ent[1] ^= 1
+        return ent[0][ent[1]]
 
     # ---- stand-ins for the two out-of-path selections -------------------------------------------------
     @staticmethod
@@ -77,7 +90,7 @@ class AttnShiftRoIHead(nn.Module):
         maps, masks = AS.update_fg_maps(torch.cat(list(map_cos_fg)).contiguous(), feats, semantic_centers_coords, obj_num_parts,
                                         inst_fg_feat, inst_bg_feat, torch.cat([b.reshape(-1, 4).float() for b in gt_bboxes]).to(dev).contiguous(),
                                         n_per_img, hp, wp, self.rng, pos_mask_thr=pos_mask_thr)
-        m_host = torch.empty(masks.shape, dtype=torch.uint8, pin_memory=True)
+        m_host = self._mask_buffer(masks.shape)
         m_host.copy_(masks, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return list(maps.split(n_per_img, dim=0)), [m.numpy() for m in m_host.split(n_per_img, dim=0)]
@@ -147,7 +160,7 @@ class AttnShiftRoIHead(nn.Module):
             m_dev = rm['mask']
             # one pinned transfer (torch's caching host allocator recycles the block) instead of one pageable copy per
             # image; the numpy arrays are views that keep the pinned tensor alive
-            m_host = torch.empty(m_dev.shape, dtype=torch.uint8, pin_memory=True)
+            m_host = self._mask_buffer(m_dev.shape)
             m_host.copy_(m_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             masks = [m.numpy() for m in m_host.split(n_per_img, dim=0)]

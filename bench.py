@@ -202,15 +202,18 @@ def run_ours(args):
     # come from the timed region itself (its last step)
     if not os.environ.get('AS_BENCH_NO_TIMERS'):
         ops.TIMERS.enable()
+    # the clock sampler starts BEFORE the warm-up: the first NVML queries of a process are slow and take a driver lock that
+    # stalls kernel launches (seen as a 100+ ms hiccup in whichever loop ran first); its samples are reset when timing starts
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 1)):
         ops.TIMERS.begin_step()
         one_step(bb, head, img_dev, inputs, False)
     torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.rows = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
