@@ -4,14 +4,18 @@
 // attention-shift head).  The [B,h,T,T] probability tensor (845 MB / image / layer at 1024^2) is never materialised.
 //
 // as_mhsa_fwd      : flash-style forward. One CTA = one (batch, head, 128-query tile); 2 CTAs co-reside per SM.
-//                    warp 0 TMA producer (Q once, K / V^T tiles through a 2-stage ring), warp 1 tcgen05.mma issuer
-//                    (S = Q K^T into TMEM, O += P V with P read from TMEM), warps 2..5 one softmax thread per query row
-//                    (tcgen05.ld S, online max / exp2 / sum, fp16 P back into TMEM, O rescale in TMEM).
-//                    Outputs O [B,T,C] fp16 and the per-row log2-domain max m and denominator l [B,h,T].
+//                    warp 0 TMA producer (Q once, K and V^T tiles through separate 2-stage rings), warp 1 tcgen05.mma
+//                    issuer (S = Q K^T into TMEM, O += P V with P read from TMEM), warps 2..5 one softmax thread per
+//                    query row.  Default schedule (mhsa_fwd2_kernel<4,1>): one pass over S per tile, no row maximum in
+//                    the common case, P handed back in two halves, packed fp32x2 math, a quarter of the exponentials
+//                    as an FMA polynomial; mhsa_fwd_kernel is the first-generation two-pass schedule (variant 1).
+//                    Outputs O [B,T,C] fp16 and the per-row log2-domain offset m and denominator l [B,h,T].
 // as_attn_headmean : second pass for layers whose attention map is consumed: for a (128 x 128) tile loops the heads,
 //                    recomputes S_h on tensor cores and accumulates exp2(S_h*c - m_h) / l_h in registers; writes the
 //                    head-mean tile once (+ deterministic row-sum partials for the roll-out normaliser, and optionally
 //                    the transposed map as a split-fp16 pair = the K-major B operand of the roll-out GEMM).
+//                    Default: attn_headmean2_kernel, persistent (one CTA per SM walks a range of tiles, TMA / MMA run
+//                    ahead across tile borders, per-warp staged epilogue); attn_headmean_kernel = one CTA per tile.
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>

@@ -5,10 +5,12 @@
 //
 // Structure (one CTA per SM, persistent; thread-block clusters of 2 CTAs = one CTA pair per 256x256 output tile, each CTA
 // owning 128 rows of it):
-//   warp 0      : TMA producer  -- X and W tiles (64 halves = 128 B rows, SWIZZLE_128B) into a 4-stage smem ring
-//   warp 1      : MMA issuer    -- tcgen05.mma.cta_group::2.kind::f16 (M256 N256 K16 across the pair), fp32 accumulators in TMEM, 2 accumulator
-//                                  buffers (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of i+1
-//   warps 2..9  : epilogue      -- tcgen05.ld 32x32b, bias / GELU / residual / QKV head split, vector stores
+//   warp 0      : TMA producer  -- X and W tiles (64 halves = 128 B rows, SWIZZLE_128B) into a 6-stage smem ring
+//   warp 1      : MMA issuer    -- tcgen05.mma.cta_group::2.kind::f16 (M256 N256 K16 across the pair), fp32 accumulators in
+//                                  TMEM, 2 accumulator buffers (2 x 256 columns): the epilogue of tile i overlaps the mainloop of i+1
+//   warps 2..9  : epilogue      -- tcgen05.ld 32x32b, bias / GELU / residual / QKV head split; every 32 x 32 chunk crosses a
+//                                  private XOR-swizzled smem tile so that the global stores (and residual loads) cover whole
+//                                  row segments; the epilogue mode is a template parameter
 #include "common.cuh"
 
 using namespace asb;
