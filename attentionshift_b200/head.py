@@ -6,8 +6,9 @@ Registered under BOTH names the reference configs use (``AttnShiftRoIHead`` in c
 ``seed_pseudo_gt`` keeps the reference signature and return keys; its body runs on the sm_100a kernels through
 ``attention_shift``.  The two learned / host-side selections that sit in the middle of the reference function are
 outside this path and enter through hooks:
-  * point-token <-> GT matching (HungarianPointAssigner, scipy on the host in the reference): ``pos_inds`` kwarg, or the
-    built-in L1 Hungarian stand-in on the host;
+  * point-token <-> GT matching (HungarianPointAssigner + PointPseudoSampler, scipy on the host in the reference): done
+    the same way on the host (``assigner.py``, pinned against the reference classes), or bypassed with the ``pos_inds``
+    kwarg (instances then pair ``pos_inds[i][j]`` with ``gt_points[i][j]``);
   * the MIL layer choice (RoIAlign + MAEBoxHeadMIL, RH:2953-2972): ``gt_index`` kwarg or ``mil_fn`` callable.
 The loss-side methods of the reference class (forward_train / simple_test) are not part of the hot path.
 """
@@ -27,6 +28,13 @@ class AttnShiftRoIHead(nn.Module):
         super().__init__()
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg
+        # CFG:182-187 point_assigner: FocalLossCost weight 1, PointL1Cost weight 10, times 1
+        pa = (train_cfg.get('point_assigner') if hasattr(train_cfg, 'get') else None) or {}
+        self.point_cls_weight = float((pa.get('cls_cost') or {}).get('weight', 1.0))
+        self.point_reg_weight = float((pa.get('reg_cost') or {}).get('weight', 10.0))
+        self.point_times = int(pa.get('times', 1))
+        if self.point_times != 1:
+            raise ValueError('point_assigner.times > 1 is not part of the hot path (the shipped config uses 1)')
         cfg = bbox_head if isinstance(bbox_head, dict) else {}
         # CFG:102-105 -- the reference reads these off ``self.bbox_head``
         self.cam_layer = int(cfg.get('cam_layer', 7))
@@ -58,21 +66,21 @@ class AttnShiftRoIHead(nn.Module):
         ent[1] ^= 1
         return ent[0][ent[1]]
 
-    # ---- stand-ins for the two out-of-path selections -------------------------------------------------
-    @staticmethod
-    def match_points(point_reg, gt_points, imgs_wh):
-        """Host Hungarian on the L1 distance between predicted (normalised) points and GT points -- the geometric term of
-        HungarianPointAssigner (hungarian_point_assigner.py:53-109).  -> list of LongTensor pos_inds (gt order)."""
-        from scipy.optimize import linear_sum_assignment
-        out = []
-        for i in range(point_reg.shape[0]):
-            pred = point_reg[i].detach().float().cpu()
-            gt = (gt_points[i].detach().float().cpu() / imgs_wh[i].detach().float().cpu().reshape(1, 2))
-            cost = torch.cdist(pred, gt, p=1)
-            r, c = linear_sum_assignment(cost.numpy())
-            order = torch.as_tensor(c).argsort()
-            out.append(torch.as_tensor(r)[order].long())
-        return out
+    # ---- the two selections that sit next to the device path ---------------------------------------------
+    def match_points(self, point_reg, point_cls, gt_points, gt_labels, imgs_wh):
+        """RH:2237-2257: the reference's HungarianPointAssigner + PointPseudoSampler per image (``assigner.py``; host + scipy
+        like the reference).  -> (pos_inds, pos_gt): per image the matched point tokens in ascending order and the GT each
+        one belongs to."""
+        from .assigner import hungarian_point_assign
+        reg = point_reg.detach().float().cpu()
+        cls = point_cls.detach().float().cpu()
+        pos, pgt = [], []
+        for i in range(reg.shape[0]):
+            p_i, g_i = hungarian_point_assign(reg[i], cls[i], gt_points[i].detach().float().cpu(), gt_labels[i].detach().cpu().long(),
+                                              imgs_wh[i], self.point_cls_weight, self.point_reg_weight, self.point_times)
+            pos.append(p_i)
+            pgt.append(g_i)
+        return pos, pgt
 
     @torch.no_grad()
     def update_fg_map(self, map_cos_fg, map_cos_bg, vit_feat, semantic_centers_coords, obj_num_parts, inst_fg_feat, inst_bg_feat,
@@ -109,8 +117,17 @@ class AttnShiftRoIHead(nn.Module):
         B = feats.shape[0]
         n_prop = point_cls.size(1) if point_cls is not None else attns[-1].shape[1] - 1 - hp * wp
         if pos_inds is None:
-            wh = imgs_whwh.reshape(B, -1)[:, :2] if imgs_whwh is not None else torch.tensor([[wp * 16., hp * 16.]]).repeat(B, 1)
-            pos_inds = self.match_points(point_reg, gt_points, wh)
+            # RH:2237-2257: Hungarian match of the point tokens to the GT points; instances then follow the matched TOKEN
+            # order and carry the point / label of the GT they were matched to (get_targets + labels[i][pos_inds])
+            if img_metas is not None and all('img_shape' in m for m in img_metas):
+                wh = [(m['img_shape'][1], m['img_shape'][0]) for m in img_metas]
+            elif imgs_whwh is not None:
+                wh = [tuple(v) for v in imgs_whwh.reshape(B, -1)[:, :2].tolist()]
+            else:
+                wh = [(wp * 16., hp * 16.)] * B
+            pos_inds, pos_gt = self.match_points(point_reg, point_cls, gt_points, gt_points_labels, wh)
+            gt_points = [gt_points[i][pos_gt[i].to(gt_points[i].device)] for i in range(B)]
+            gt_points_labels = [gt_points_labels[i][pos_gt[i].to(gt_points_labels[i].device)] for i in range(B)]
         n_per_img = [int(p.shape[0]) for p in pos_inds]
         n_tot = sum(n_per_img)
         obj_img = AS.instance_image_index(n_per_img, dev)

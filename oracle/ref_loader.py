@@ -124,3 +124,41 @@ def load_rh():
     out.methods = types.SimpleNamespace(**methods)
     _cache["rh"] = out
     return out
+
+
+def load_point_assigner():
+    """-> (HungarianPointAssigner class, PointPseudoSampler class) of the reference, AST-extracted with stubs for the mmdet
+    registries (``BBOX_ASSIGNERS``, ``MATCH_COST``, ``BBOX_SAMPLERS``), ``AssignResult`` and the sampling result."""
+    if "assigner" in _cache:
+        return _cache["assigner"]
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+
+    class AssignResult:
+        def __init__(self, num_gts, gt_inds, max_overlaps, labels=None):
+            self.num_gts, self.gt_inds, self.max_overlaps, self.labels = num_gts, gt_inds, max_overlaps, labels
+
+    class PointSamplingResult:
+        def __init__(self, pos_inds, neg_inds, bboxes, gt_bboxes, assign_result, gt_flags):
+            self.pos_inds, self.neg_inds = pos_inds, neg_inds
+            self.pos_assigned_gt_inds = assign_result.gt_inds[pos_inds] - 1
+
+    ns = dict(torch=torch, MATCH_COST=_Reg(), BBOX_ASSIGNERS=_Reg(), BBOX_SAMPLERS=_Reg(), AssignResult=AssignResult,
+              BaseAssigner=object, BaseSampler=object, PointSamplingResult=PointSamplingResult, SamplingResult=object,
+              bbox_overlaps=None, bbox_cxcywh_to_xyxy=None, bbox_xyxy_to_cxcywh=None)
+    try:
+        from scipy.optimize import linear_sum_assignment
+    except ImportError:
+        linear_sum_assignment = None
+    ns["linear_sum_assignment"] = linear_sum_assignment
+    for rel in ("mmdet/core/bbox/match_costs/match_cost.py", "mmdet/core/bbox/assigners/hungarian_point_assigner.py",
+                "mmdet/core/bbox/samplers/point_pseudo_sampler.py"):
+        tree = ast.parse(open(os.path.join(REF_ROOT, rel)).read())
+        for node in tree.body:
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+                exec(compile(ast.Module(body=[node], type_ignores=[]), rel, "exec"), ns)
+    ns["build_match_cost"] = lambda cfg: ns[cfg["type"]](**{k: v for k, v in cfg.items() if k != "type"})
+    _cache["assigner"] = (ns["HungarianPointAssigner"], ns["PointPseudoSampler"])
+    return _cache["assigner"]

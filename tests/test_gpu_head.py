@@ -103,3 +103,43 @@ def test_update_fg_map_vs_oracle():
         assert masks[i].dtype.name == 'uint8' and masks[i].shape == (n, H, H)
         for j in range(n):
             assert _iou(torch.from_numpy(masks[i][j]), r_masks[i][j]) >= 0.999
+
+
+def test_seed_pseudo_gt_point_matching_like_reference():
+    """pos_inds=None: the head matches point tokens to GT points itself (HungarianPointAssigner, RH:2237-2257).  Must equal the
+    call that is handed the same match explicitly, with the GT points / labels permuted into matched-token order."""
+    from attentionshift_b200 import assigner as A
+    from attentionshift_b200 import attention_shift as AS
+    from attentionshift_b200.registry import build_head
+    embed, heads, depth, img, n_pt = 64, 1, 7, 224, 12
+    hp = img // 16
+    sd = vit_state_dict(embed, depth, heads, img, n_point_tokens=n_pt, seed=4)
+    for i in range(depth):
+        sd[f'blocks.{i}.attn.qkv.weight'] = sd[f'blocks.{i}.attn.qkv.weight'] * 12
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, img, img, generator=g)
+    ref = V.backbone_forward(x, sd, depth, heads, n_point_tokens=n_pt)
+    gt_points = [torch.tensor([[60., 80.], [150., 130.]]), torch.tensor([[100., 100.]])]
+    labels = [torch.tensor([1, 5]), torch.tensor([9])]
+    gt_index = [torch.tensor([6, 2]), torch.tensor([4])]
+    point_reg = torch.rand(2, n_pt, 2, generator=g)
+    point_cls = torch.randn(2, n_pt, 20, generator=g)
+    attns = [a.to(DEV) for a in ref['attns']]
+    vit_feat = ref['last_feat'][:, 1:].permute(0, 2, 1).unflatten(-1, (hp, hp)).to(DEV)
+    metas = [dict(img_shape=(img, img, 3))] * 2
+
+    def run(**kw):
+        head = build_head(dict(type='AttnShiftRoIHead', bbox_head=dict(cam_layer=7, seed_thr=0.2, seed_multiple=0.5),
+                               mean_shift_times_local=3, n_seeds=20, num_semantic_points=3, rng=AS.KeyedRng(11)))
+        return head.seed_pseudo_gt(None, metas, None, None, None, vit_feat=vit_feat, point_cls=point_cls.to(DEV),
+                                   point_reg=point_reg.to(DEV), attns=attns, return_mask=False, pos_mask_thr=0.6,
+                                   neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, obj_tau=0.85, gt_index=gt_index, **kw)
+
+    auto = run(gt_points=gt_points, gt_points_labels=labels)
+    pos, pgt = zip(*[A.hungarian_point_assign(point_reg[i], point_cls[i], gt_points[i], labels[i], (img, img)) for i in range(2)])
+    manual = run(gt_points=[gt_points[i][pgt[i]] for i in range(2)], gt_points_labels=[labels[i][pgt[i]] for i in range(2)],
+                 pos_inds=list(pos))
+    for i in range(2):
+        assert torch.equal(auto['pseudo_gt_bboxes'][i], manual['pseudo_gt_bboxes'][i])
+        assert torch.equal(auto['map_cos_fg'][i], manual['map_cos_fg'][i])
+        assert torch.equal(auto['pseudo_gt_labels'][i].cpu(), labels[i][pgt[i]])

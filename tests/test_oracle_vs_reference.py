@@ -98,3 +98,22 @@ def test_update_fg_map_bit_exact(hp, c, n_obj, seed):
     assert torch.equal(r_maps[0], o_maps[0])
     assert (torch.from_numpy(r_masks[0]) == o_masks[0]).all()
     assert o_maps[0].abs().sum() > 0
+
+
+@pytest.mark.parametrize('seed,n_prop,n_gt,times', [(0, 100, 3, 1), (1, 100, 7, 1), (2, 12, 12, 1), (3, 100, 2, 2)])
+def test_point_assigner_equals_reference(seed, n_prop, n_gt, times):
+    """Point-token <-> GT matching (RH:2237-2257): attentionshift_b200.assigner against the reference's
+    HungarianPointAssigner + PointPseudoSampler with the costs of configs/mae/attnshift_voc12aug.py:182-187."""
+    from attentionshift_b200 import assigner as A
+    Assigner, Sampler = ref_loader.load_point_assigner()
+    g = torch.Generator().manual_seed(seed)
+    pred = torch.rand(n_prop, 2, generator=g)
+    cls = torch.randn(n_prop, 20, generator=g) * 2
+    gtp = torch.rand(n_gt, 2, generator=g) * torch.tensor([1000., 600.])
+    lab = torch.randint(0, 20, (n_gt,), generator=g)
+    ref = Assigner(cls_cost=dict(type='FocalLossCost', weight=1.0), reg_cost=dict(type='PointL1Cost', weight=10.0), times=times)
+    ar = ref.assign(pred, cls, gtp, lab, dict(img_shape=(600, 1000, 3)))
+    sr = Sampler().sample(ar, pred, gtp)
+    pos, pos_gt = A.hungarian_point_assign(pred, cls, gtp, lab, (1000, 600), 1.0, 10.0, times)
+    assert torch.equal(pos, sr.pos_inds) and torch.equal(pos_gt, sr.pos_assigned_gt_inds)
+    assert torch.equal(lab[pos_gt], ar.labels[sr.pos_inds])
