@@ -204,8 +204,9 @@ def run_ours(args):
         ops.TIMERS.enable()
     # the clock sampler starts BEFORE the warm-up: the first NVML queries of a process are slow and take a driver lock that
     # stalls kernel launches (seen as a 100+ ms hiccup in whichever loop ran first); its samples are reset when timing starts
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None     # one per job: NVML calls serialise on a driver lock shared by all ranks
+    if sampler is not None:
+        sampler.start()
     for _ in range(max(args.warmup, 1)):
         ops.TIMERS.begin_step()
         one_step(bb, head, img_dev, inputs, False)
@@ -213,7 +214,8 @@ def run_ours(args):
 
     # ---- device-resident timing (value)
     barrier()
-    sampler.rows = []
+    if sampler is not None:
+        sampler.rows = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -260,8 +262,9 @@ def run_ours(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
 
     ms_dev, ms_e2e = parallel.max_over_ranks([ms_dev, ms_e2e], device=dev)     # the slowest rank defines the step
     n_ours, n_all = count_launches(lambda: one_step(bb, head, img_dev, inputs, False)) if rank == 0 else (None, None)
