@@ -84,8 +84,12 @@ class VisionTransformerDet(nn.Module):
             raise ValueError('the sm_100a path implements the 16x16 RGB patch embedding used by configs/mae')
         if embed_dim % num_heads or embed_dim // num_heads != 64:
             raise ValueError('head_dim must be 64 (ViT-S/B/L)')
-        if drop_rate or attn_drop_rate or drop_path_rate or init_values or qk_scale:
-            raise ValueError('dropout / drop-path / layer-scale / qk_scale are not part of the hot path')
+        if init_values or qk_scale:
+            raise ValueError('layer-scale / qk_scale are not part of the hot path (the shipped configs use neither)')
+        # configs/mae/attnshift_voc12aug.py:29 sets drop_path_rate=0.05.  Dropout and stochastic depth are the identity in
+        # inference mode, and this path is the no-grad forward (the attention-shift head consumes detached tensors, DET:77):
+        # the rates are accepted so that the reference configs build unchanged, and are not applied.
+        self.drop_rate, self.attn_drop_rate, self.drop_path_rate = float(drop_rate), float(attn_drop_rate), float(drop_path_rate)
         self.embed_dim = self.num_features = embed_dim
         self.num_heads = num_heads
         self.patch_size = patch_size

@@ -117,3 +117,22 @@ def test_point_assigner_equals_reference(seed, n_prop, n_gt, times):
     pos, pos_gt = A.hungarian_point_assign(pred, cls, gtp, lab, (1000, 600), 1.0, 10.0, times)
     assert torch.equal(pos, sr.pos_inds) and torch.equal(pos_gt, sr.pos_assigned_gt_inds)
     assert torch.equal(lab[pos_gt], ar.labels[sr.pos_inds])
+
+
+def test_reference_config_builds_unchanged():
+    """configs/mae/attnshift_voc12aug.py: the `backbone` and `roi_head` dicts build through this repo's registry as they are
+    (mmdet passes train_cfg.rcnn / test_cfg.rcnn to the RoI head), and the values the hot path reads arrive."""
+    import os
+    from attentionshift_b200 import registry
+    ns = {}
+    exec(open(os.path.join(ref_loader.REF_ROOT, 'configs/mae/attnshift_voc12aug.py')).read(), ns)
+    m = ns['model']
+    bb = registry.build_backbone(dict(m['backbone']))
+    assert bb.embed_dim == 384 and bb.num_heads == 6 and len(bb.blocks) == 12 and bb.point_tokens_num == 100
+    assert bb.return_attention and bb.last_feat and bb.drop_path_rate == 0.05
+    hd = registry.build_head(dict(m['roi_head'], train_cfg=m['train_cfg']['rcnn'], test_cfg=m['test_cfg']['rcnn']))
+    assert (hd.cam_layer, hd.seed_thr, hd.seed_multiple) == (7, 0.2, 0.5)
+    assert (hd.num_semantic_points, hd.mean_shift_times_local) == (5, 10)
+    assert (hd.point_cls_weight, hd.point_reg_weight, hd.point_times) == (1.0, 10.0, 1)
+    # the second registry name of the same class (the reference's rename is incomplete)
+    assert type(registry.build_head(dict(m['roi_head'], type='StandardRoIHeadMaskPointSampleDeformAttnReppoints'))) is type(hd)
