@@ -412,6 +412,30 @@ def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=
     return st
 
 
+def select_seed_candidates(kind, inst, row, totals, ks, P, n_rows, gt_points_fn):
+    """Host half of RH:343-371 once the candidate counts are known (pure numpy, CPU-tested against the oracle).
+    kind [n_items] (1 = foreground item), inst [n_items] instance whose GT point pads a short foreground item, row [n_items]
+    destination row of the [n_rows, P, 2] point table, totals [n_items] candidate counts, ks [n_items, P] drawn candidate
+    ranks (``randint(total)[:P]``).  -> (pts_host [n_rows,P,2] int32: the GT fill, zeros elsewhere; sel_item, sel_k: which
+    candidate (row-major rank) of which item the device has to look up; sel_dst: its flat slot in the point table).
+    A foreground item with fewer than P candidates takes all of them and repeats the GT point (RH:354-358) -- in (y, x)
+    order: the reference appends the (x, y) point to (row, col) candidates and flips the last dimension of everything."""
+    n_items = len(kind)
+    short = (kind == 1) & (totals < P)
+    slot_j = np.arange(P)[None, :]
+    ks = np.where(short[:, None], slot_j, ks)
+    use = ~short[:, None] | (slot_j < totals[:, None])       # which of the P slots are real candidates
+    pts_host = np.zeros((n_rows, P, 2), dtype=np.int32)
+    if short.any():
+        gtp = gt_points_fn().astype(np.int32)                # int(float) truncation, as the reference's .long()
+        for i in np.nonzero(short)[0]:
+            pts_host[row[i], int(totals[i]):] = gtp[inst[i]][::-1]
+    sel_item = np.broadcast_to(np.arange(n_items)[:, None], (n_items, P))[use]
+    sel_k = ks[use]
+    sel_dst = (row[:, None] * P + slot_j)[use]
+    return pts_host, sel_item, sel_k, sel_dst
+
+
 def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng, thr_pos=0.2, thr_neg=0.1,
                  num_points=20, refine_times=2, obj_tau=0.85, mask_thr=0.6, want_bg=True, want_mask=True, begun=None):
     """RH:1000-1019 for every instance of the batch.
@@ -458,17 +482,8 @@ def refined_maps(cam_low, cam_mm, feats, n_per_img, rois, gt_points, hp, wp, rng
             num = int(totals[i])
             n_draw = len(range(0, num, num // P))
             ks[i] = (rng.randint(st['keys'][i], num, n_draw) % num)[:P].numpy()
-    slot_j = np.arange(P)[None, :]
-    ks = np.where(short[:, None], slot_j, ks)
-    use = ~short[:, None] | (slot_j < totals[:, None])       # which of the P slots are real candidates
-    pts_host = np.zeros((grp.G * grp.S, P, 2), dtype=np.int32)
-    if short.any():
-        gtp = gt_points.detach().cpu().numpy().astype(np.int32)      # int(float) truncation, as the reference's .long()
-        for i in np.nonzero(short)[0]:
-            pts_host[np_row[i], int(totals[i]):] = gtp[np_a[i]]
-    sel_item = np.broadcast_to(np.arange(n_items)[:, None], (n_items, P))[use]
-    sel_k = ks[use]
-    sel_dst = (np_row[:, None] * P + slot_j)[use]
+    pts_host, sel_item, sel_k, sel_dst = select_seed_candidates(np_kind, np_a, np_row, totals, ks, P, grp.G * grp.S,
+                                                                lambda: gt_points.detach().cpu().numpy())
     n_sel = int(sel_item.size)
     pts, d_item, d_k, d_dst = _upload_i32([pts_host, sel_item, sel_k, sel_dst], dev)
     pts = pts.view(grp.G, grp.S, P, 2)
