@@ -220,6 +220,16 @@ class _Pending:
             self.token = None
         return self.host
 
+    def __del__(self):
+        # never read: hand the ring region back (behind an event, the copy may still be in flight) instead of leaving it
+        # marked busy for good
+        try:
+            if self.token is not None:
+                self.ring.done(self.token)
+                self.token = None
+        except Exception:
+            pass
+
 
 _OBJ_IMG = {}
 
@@ -552,7 +562,7 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
     sel_obj, sel_kind, sel_k, sel_dst = [], [], [], []
     coords = np.zeros((n_tot, num_gt, 2), dtype=np.float32)
     labels = np.zeros((n_tot, num_gt), dtype=np.bool_)
-    rois_i = None
+    rois_i = st['pending_rois'].get()                         # enqueued right behind the counts: on the host by now
     for o, key in enumerate(keys):
         n_pos, n_neg = int(totals[o, 0]), int(totals[o, 1])
         tot = n_pos + n_neg
@@ -562,7 +572,6 @@ def mask_points(map_fg, map_bg, rois, n_per_img, rng, pos_thr=0.6, neg_thr=0.6, 
             chosen = rng.randperm_head(key, tot, num_gt).tolist()
         if len(chosen) < num_gt:
             if len(chosen) == 0:                             # RH:452-455 sentinel (-1,-1), then the crop offset is added
-                rois_i = st['pending_rois'].get() if rois_i is None else rois_i
                 coords[o, :, 0] = -1.0 + float(rois_i[o, 0])
                 coords[o, :, 1] = -1.0 + float(rois_i[o, 1])
                 continue
