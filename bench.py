@@ -104,6 +104,29 @@ class ClockSampler(threading.Thread):
                     source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
+def usable_cpus():
+    """Host cores this process may actually use: the affinity mask and the cgroup CPU quota, not the machine's core count
+    (128 torch threads on a container throttled to a few cores made the CPU arm 10x slower than 16 threads on 16 cores)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if quota not in ('max', '-1'):
+                n = min(n, max(1, int(float(quota) / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -180,7 +203,7 @@ def run_ours(args):
         os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line the driver parses
     rank, world, local = parallel.env_rank_world()
     # the host side of a rank is one launching thread: keep torch's CPU pool from oversubscribing the box when 8 ranks share it
-    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 8) // max(world, 1))))
+    torch.set_num_threads(max(1, min(4, usable_cpus() // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     parallel.init('nccl', dev)
@@ -356,10 +379,10 @@ def cpu_one_image(cfg, seed):
 
 
 def cpu_baseline(cfg, steps=1):
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cpus())
     ts = [cpu_one_image(cfg, 100 + i) for i in range(steps)]
     tot = sum(t[0] for t in ts) / len(ts)
-    return dict(value=round(1.0 / tot, 4), unit='images/s', cores=os.cpu_count(), kind='port',
+    return dict(value=round(1.0 / tot, 4), unit='images/s', cores=usable_cpus(), kind='port',
                 sample=f'{steps} image(s) of the workload (1/{cfg["batch"]} batch): ViT forward {ts[0][1]:.1f}s + roll-out/attention-shift {ts[0][2]:.1f}s; '
                        'torch CPU fp32, all host threads; attention-shift stage on the structured synthetic scene (20 seeds as hard-coded in the reference)')
 
@@ -371,7 +394,7 @@ def run_reference(args):
     cfg = dict(WORKLOAD)
     if args.small:
         cfg.update(batch=2, img=224, depth=2)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cpus())
     budget = 240.0
     t_all = time.time()
     done_w = 0
@@ -390,7 +413,7 @@ def run_reference(args):
                 dtype='f32', data='synthetic (same generator as the CUDA arm)',
                 config=dict(workload=cfg['name'], per_gpu_batch=cfg['batch'], small=bool(args.small),
                             note='each step = ONE image of the batch (bounded sample); the reference algorithm is per-image, images/s is per host'),
-                cpu_baseline=dict(value=v, unit='images/s', cores=os.cpu_count(), kind='port',
+                cpu_baseline=dict(value=v, unit='images/s', cores=usable_cpus(), kind='port',
                                   sample='one image per step; oracle port of the reference (the python reference cannot travel to the GPU box)'),
                 e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
