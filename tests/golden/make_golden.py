@@ -89,6 +89,25 @@ def update_fg_case(hp, c, n_obj, scene_seed, rng_seed):
                 masks_packed=torch.from_numpy(__import__('numpy').packbits(masks[0])))
 
 
+def assigner_case(seeds=((0, 100, 3), (1, 100, 7), (2, 12, 12), (3, 50, 1))):
+    """Point-token <-> GT matching (RH:2237-2257): the reference's HungarianPointAssigner + PointPseudoSampler with the costs
+    of configs/mae/attnshift_voc12aug.py:182-187 on random predictions."""
+    Assigner, Sampler = ref_loader.load_point_assigner()
+    ref = Assigner(cls_cost=dict(type='FocalLossCost', weight=1.0), reg_cost=dict(type='PointL1Cost', weight=10.0), times=1)
+    cases = []
+    for seed, n_prop, n_gt in seeds:
+        g = torch.Generator().manual_seed(seed)
+        pred = torch.rand(n_prop, 2, generator=g)
+        cls = torch.randn(n_prop, 20, generator=g) * 2
+        gtp = torch.rand(n_gt, 2, generator=g) * torch.tensor([1000., 600.])
+        lab = torch.randint(0, 20, (n_gt,), generator=g)
+        ar = ref.assign(pred, cls, gtp, lab, dict(img_shape=(600, 1000, 3)))
+        sr = Sampler().sample(ar, pred, gtp)
+        cases.append(dict(pred=pred, cls=cls, gt_points=gtp, gt_labels=lab, img_wh=(1000, 600), pos_inds=sr.pos_inds.clone(),
+                          pos_gt=sr.pos_assigned_gt_inds.clone()))
+    return dict(meta=dict(torch=str(torch.__version__)), cases=cases)
+
+
 def rollout_case(t, layers, b, seed):
     rh = ref_loader.load_rh()
     gen = torch.Generator().manual_seed(seed)
@@ -123,6 +142,7 @@ if __name__ == '__main__':
     torch.save(attnshift_case(28, 64, 3, scene_seed=3, rng_seed=7, noise=0.4, n_shift=10, keep_maps=False),
                os.path.join(OUT, 'attnshift_448_c64.pt'))
     torch.save(update_fg_case(20, 48, 3, scene_seed=9, rng_seed=10), os.path.join(OUT, 'update_fg_320_c48.pt'))
+    torch.save(assigner_case(), os.path.join(OUT, 'point_assigner.pt'))
     torch.save(rollout_case(t=61, layers=7, b=2, seed=1), os.path.join(OUT, 'rollout_t61.pt'))
     torch.save(vit_case(embed=128, heads=2, depth=2, img=64, n_pt=12, seed=0), os.path.join(OUT, 'vit_e128_d2.pt'))
     for f in sorted(os.listdir(OUT)):

@@ -121,3 +121,13 @@ def test_update_fg_map(golden_dir):
     packed = torch.from_numpy(np.packbits(masks[0].numpy()))
     # the masks threshold the maps at 0.6 x max: bit-equal with the same torch build
     assert (packed != g['masks_packed']).float().mean().item() < 1e-3
+
+
+def test_point_assigner(golden_dir):
+    """Point-token <-> GT matching (RH:2237-2257): attentionshift_b200.assigner against the stored outputs of the reference's
+    HungarianPointAssigner + PointPseudoSampler."""
+    from attentionshift_b200 import assigner as A
+    g = torch.load(os.path.join(golden_dir, 'point_assigner.pt'))
+    for c in g['cases']:
+        pos, pos_gt = A.hungarian_point_assign(c['pred'], c['cls'], c['gt_points'], c['gt_labels'], c['img_wh'], 1.0, 10.0, 1)
+        assert torch.equal(pos, c['pos_inds']) and torch.equal(pos_gt, c['pos_gt'])
