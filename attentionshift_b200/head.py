@@ -9,7 +9,9 @@ outside this path and enter through hooks:
   * point-token <-> GT matching (HungarianPointAssigner + PointPseudoSampler, scipy on the host in the reference): done
     the same way on the host (``assigner.py``, pinned against the reference classes), or bypassed with the ``pos_inds``
     kwarg (instances then pair ``pos_inds[i][j]`` with ``gt_points[i][j]``);
-  * the MIL layer choice (RoIAlign + MAEBoxHeadMIL, RH:2953-2972): ``gt_index`` kwarg or ``mil_fn`` callable.
+  * the MIL layer choice (RoIAlign + MAEBoxHeadMIL, RH:2953-2972): ``gt_index`` kwarg, or a ``mil_fn`` callable that gets
+    the per-layer pseudo boxes exactly as the reference hands them to ``_mil_forward_train`` (``mil_from_reference`` wraps the
+    reference head's own MIL stage; its losses come back under ``mil_losses``).
 The loss-side methods of the reference class (forward_train / simple_test) are not part of the hot path.
 """
 import torch
@@ -82,6 +84,26 @@ class AttnShiftRoIHead(nn.Module):
             pgt.append(g_i)
         return pos, pgt
 
+    def _mil_select(self, boxes, n_per_img, gt_labels, roi_feature_map, img_metas):
+        """RH:2308-2312: hand the per-layer pseudo boxes to the MIL head and take its layer choice.  boxes [L, n_tot, 4].
+        ``mil_fn(boxes_per_img, gt_labels, roi_feature_map, img_metas)`` gets the boxes as the reference builds them (per
+        image [n_i, L, 4], RH:2296-2306) and may return the layer index per instance (tensor or per-image list), a pair
+        ``(index, losses)``, or the reference's ``_mil_forward_train(..., return_index=True)`` triple
+        ``(boxes, losses, index)`` -- see ``mil_from_reference``.  -> (gt_index [n_tot] long on the device, losses dict)."""
+        per_img = list(boxes.permute(1, 0, 2).split(list(n_per_img), dim=0))
+        out = self.mil_fn(per_img, gt_labels, roi_feature_map, img_metas)
+        losses = {}
+        if isinstance(out, tuple) and len(out) == 3:
+            _, losses, idx = out
+        elif isinstance(out, tuple) and len(out) == 2:
+            idx, losses = out
+        else:
+            idx = out
+        idx = torch.cat([g.reshape(-1) for g in idx]) if isinstance(idx, (list, tuple)) else idx.reshape(-1)
+        if idx.numel() != sum(n_per_img):
+            raise ValueError(f'mil_fn returned {idx.numel()} layer indices for {sum(n_per_img)} instances')
+        return idx.to(boxes.device).long(), dict(losses)
+
     @torch.no_grad()
     def update_fg_map(self, map_cos_fg, map_cos_bg, vit_feat, semantic_centers_coords, obj_num_parts, inst_fg_feat, inst_bg_feat,
                       gt_bboxes, pos_mask_thr):
@@ -142,6 +164,7 @@ class AttnShiftRoIHead(nn.Module):
         lab_sizes = [int(l.numel()) for l in gt_points_labels[:B]]
         labels = list(torch.cat([l.reshape(-1) for l in gt_points_labels[:B]]).to(dev, non_blocking=True).split(lab_sizes))
         # ^ RH:2269 labels[i][pos_inds]: one label per matched GT
+        mil_losses = {}
         # A5-A7
         rows = AS.rollout_rows(list(attns[-self.cam_layer:]), n_prop)
         cams, mm = AS.cam_maps(rows, obj_img, obj_pt, hp, wp)
@@ -155,9 +178,7 @@ class AttnShiftRoIHead(nn.Module):
         if gt_index is None:
             if self.mil_fn is None:
                 raise ValueError('seed_pseudo_gt needs gt_index= or a mil_fn (MIL head is outside the hot path)')
-            gt_index = self.mil_fn(boxes.permute(1, 0, 2))
-            gt_index = torch.cat([g.reshape(-1) for g in gt_index]) if isinstance(gt_index, (list, tuple)) else gt_index
-            gt_index = gt_index.to(dev).long()
+            gt_index, mil_losses = self._mil_select(boxes, n_per_img, labels, roi_feature_map, img_metas)
             begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
         pseudo_boxes = boxes[gt_index, ar].contiguous()                # RH:2965-2967 gather of the chosen layer's box
         # A8, A13
@@ -186,7 +207,7 @@ class AttnShiftRoIHead(nn.Module):
         grp = rm['groups']
         fg_feat = [rm['centroid'][g, :n + 1].reshape(n + 1, -1, 1, 1) for g, n in enumerate(n_per_img)]
         bg_feat = [rm['centroid'][g, n + 1:2 * n + 1].reshape(n, -1, 1, 1) for g, n in enumerate(n_per_img)]
-        out = dict(pseudo_gt_labels=labels, pseudo_gt_bboxes=split(pseudo_boxes), mil_losses={},
+        out = dict(pseudo_gt_labels=labels, pseudo_gt_bboxes=split(pseudo_boxes), mil_losses=mil_losses,
                    best_attn_idx=split(gt_index), map_cos_fg=split(rm['map_fg']),
                    mask_points_coords=split(coords), mask_points_labels=split(plabels),
                    semantic_centers=[p['semantic_centers'] for p in per_img],
@@ -203,3 +224,15 @@ class AttnShiftRoIHead(nn.Module):
                        points_bg=rm['pts'], points_fg=rm['pts'])
         self._last = dict(rows=rows, cams=cams, boxes=boxes, refined=rm, parts=parts)
         return out
+
+
+def mil_from_reference(ref_head):
+    """``mil_fn`` that defers to the REFERENCE RoI head's MIL stage (``_mil_forward_train``, RH:2953-2972: RoIAlign over the
+    7 x n_gt pseudo boxes + MAEBoxHeadMIL), for running this repo's ``seed_pseudo_gt`` inside the reference detector:
+
+        fast = build_head(dict(cfg.model.roi_head, train_cfg=cfg.model.train_cfg.rcnn, mil_fn=mil_from_reference(ref_head)))
+        ref_head.seed_pseudo_gt = fast.seed_pseudo_gt          # losses / test-time methods stay the reference's
+    """
+    def fn(boxes_per_img, gt_labels, roi_feature_map, img_metas):
+        return ref_head._mil_forward_train(roi_feature_map, None, boxes_per_img, gt_labels, img_metas, return_index=True)
+    return fn
