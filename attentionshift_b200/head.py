@@ -196,8 +196,8 @@ class AttnShiftRoIHead(nn.Module):
         split = lambda t: list(t.split(n_per_img, dim=0))
         if return_mask:                                         # RH:2358 hand-off: uint8 numpy masks on the host
             m_dev = rm['mask']
-            # one pinned transfer (torch's caching host allocator recycles the block) instead of one pageable copy per
-            # image; the numpy arrays are views that keep the pinned tensor alive
+            # one transfer into a persistent pinned buffer (two alternate, see _mask_buffer) instead of one pageable copy per
+            # image; the numpy arrays are views of it
             m_host = self._mask_buffer(m_dev.shape)
             m_host.copy_(m_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
