@@ -47,3 +47,17 @@ def test_ring_oversize_request_bypasses_the_arena():
     r = R(1024)
     v, t = r.take(5000)
     assert t is None and v.numel() >= 5000 and r.head == 0
+
+
+def test_packed_upload_slices_and_shapes(monkeypatch):
+    """_upload_i32: several host arrays travel as ONE buffer and come back as int32 views of the right shapes (the fp32
+    bit-pattern trick used for coordinates included)."""
+    import numpy as np
+    ring = _Ring(1 << 16)
+    monkeypatch.setattr(AS, '_ring', lambda dev: ring)
+    coords = np.array([[1.5, -2.25], [3.0, 4.0]], dtype=np.float32)
+    a, b, c, d = AS._upload_i32([[1, 2, 3], np.arange(6).reshape(2, 3), coords.view(np.int32), []], torch.device('cpu'))
+    assert a.tolist() == [1, 2, 3] and b.shape == (2, 3) and b.tolist() == [[0, 1, 2], [3, 4, 5]]
+    assert torch.equal(c.view(torch.float32), torch.from_numpy(coords)) and d.numel() == 0
+    assert all(t.dtype == torch.int32 for t in (a, b, c, d))
+    assert len(ring.inflight) == 1 and ring.inflight[0][2] is not None      # one region, marked done after the copy
