@@ -11,7 +11,9 @@ outside this path and enter through hooks:
     kwarg (instances then pair ``pos_inds[i][j]`` with ``gt_points[i][j]``);
   * the MIL layer choice (RoIAlign + MAEBoxHeadMIL, RH:2953-2972): ``gt_index`` kwarg, or a ``mil_fn`` callable that gets
     the per-layer pseudo boxes exactly as the reference hands them to ``_mil_forward_train`` (``mil_from_reference`` wraps the
-    reference head's own MIL stage; its losses come back under ``mil_losses``).
+    reference head's own MIL stage; its losses come back under ``mil_losses``), or -- when the config carries a
+    ``mil_head=dict(type='MAEBoxHeadMIL', ...)`` -- this repo's restatement of that stage (``mil.py``: torchvision RoIAlign +
+    the same four Linear layers, parameter names as in the reference).
 The loss-side methods of the reference class (forward_train / simple_test) are not part of the hot path.
 """
 import torch
@@ -51,6 +53,16 @@ class AttnShiftRoIHead(nn.Module):
         self.mean_shift_times_local = mean_shift_times_local
         self.n_seeds = n_seeds                  # 20 in the reference (hard-coded at RH:2024)
         self.mil_fn = mil_fn
+        if mil_fn is None and isinstance(mil_head, dict) and mil_head.get('type') == 'MAEBoxHeadMIL':
+            # the reference builds ``self.mil_head`` from this dict (RH:1352-1356) and RoIAligns with ``bbox_roi_extractor``
+            # (CFG:64-68: output 7, stride 16); same attribute name, same parameter names -> checkpoints load
+            from . import mil as _mil
+            from .registry import build_head
+            self.mil_head = build_head(dict(mil_head))
+            rex = bbox_roi_extractor if isinstance(bbox_roi_extractor, dict) else {}
+            stride = int((rex.get('featmap_strides') or [16])[0])
+            rsize = int((rex.get('roi_layer') or {}).get('output_size', self.mil_head.roi_size))
+            self.mil_fn = lambda boxes, labels, fmap, metas: _mil.mil_select(self.mil_head, fmap, boxes, labels, stride, rsize)
         self.rng = rng if rng is not None else AS.KeyedRng(0)
         self.with_mil = mil_head is not None or mil_fn is not None
         self.with_deform_sup = False

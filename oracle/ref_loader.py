@@ -162,3 +162,34 @@ def load_point_assigner():
     ns["build_match_cost"] = lambda cfg: ns[cfg["type"]](**{k: v for k, v in cfg.items() if k != "type"})
     _cache["assigner"] = (ns["HungarianPointAssigner"], ns["PointPseudoSampler"])
     return _cache["assigner"]
+
+
+def load_mil_head():
+    """-> the reference class MAEBoxHeadMIL (mae_bbox_head_mil.py:18-169), AST-extracted; its mmdet base class ``BBoxHead`` is
+    replaced by a stub that only keeps ``num_classes`` (the shipped config builds it with ``with_cls=False, with_reg=False``,
+    so the base contributes no parameters)."""
+    if "mil" in _cache:
+        return _cache["mil"]
+    vt = load_vt()
+    from functools import partial
+    from collections import OrderedDict
+
+    class BBoxHead(nn.Module):
+        def __init__(self, num_classes=80, **kwargs):
+            super().__init__()
+            self.num_classes = num_classes
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+
+    ns = dict(torch=torch, nn=nn, F=F, os=os, math=math, partial=partial, OrderedDict=OrderedDict, HEADS=_Reg(), BBoxHead=BBoxHead,
+              Block=vt.Block, trunc_normal_=vt.trunc_normal_, get_root_logger=lambda *a, **k: None,
+              _load_checkpoint=None, load_state_dict=None, checkpoint=None)
+    rel = "mmdet/models/roi_heads/bbox_heads/mae_bbox_head_mil.py"
+    tree = ast.parse(open(os.path.join(REF_ROOT, rel)).read())
+    for node in tree.body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), rel, "exec"), ns)
+    _cache["mil"] = ns["MAEBoxHeadMIL"]
+    return _cache["mil"]

@@ -136,3 +136,26 @@ def test_reference_config_builds_unchanged():
     assert (hd.point_cls_weight, hd.point_reg_weight, hd.point_times) == (1.0, 10.0, 1)
     # the second registry name of the same class (the reference's rename is incomplete)
     assert type(registry.build_head(dict(m['roi_head'], type='StandardRoIHeadMaskPointSampleDeformAttnReppoints'))) is type(hd)
+
+
+def test_mil_head_equals_reference():
+    """MIL layer selection (MAEBoxHeadMIL, mae_bbox_head_mil.py:140-169) with the shipped config's sizes: same parameters in,
+    same layer choice and loss out."""
+    from attentionshift_b200 import registry
+    import attentionshift_b200.mil  # noqa: F401  (registers MAEBoxHeadMIL)
+    Ref = ref_loader.load_mil_head()
+    cfg = dict(in_channels=384, img_size=224, patch_size=16, embed_dim=256, depth=4, num_heads=8, mlp_ratio=4., num_classes=20,
+               num_layers_query=7, loss_mil_factor=1.0, hidden_dim=1024, roi_size=7)
+    torch.manual_seed(0)
+    ref = Ref(pretrained=True, use_checkpoint=False, **cfg).eval()
+    ours = registry.build_head(dict(type='MAEBoxHeadMIL', pretrained=True, use_checkpoint=False, with_cls=False, with_reg=False, **cfg)).eval()
+    missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing and not unexpected
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5 * 7, 384, 7, 7, generator=g)
+    labels = [torch.tensor([3, 19]), torch.tensor([0, 7, 7])]
+    with torch.no_grad():
+        r_idx, r_loss = ref(x.clone(), gt_labels=[l.clone() for l in labels])
+        o_idx, o_loss = ours(x.clone(), gt_labels=labels)
+    assert torch.equal(r_idx, o_idx) and torch.equal(r_loss, o_loss)
+    assert o_idx.shape == (5,) and int(o_idx.max()) < 7
