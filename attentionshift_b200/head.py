@@ -57,8 +57,7 @@ class AttnShiftRoIHead(nn.Module):
             # the reference builds ``self.mil_head`` from this dict (RH:1352-1356) and RoIAligns with ``bbox_roi_extractor``
             # (CFG:64-68: output 7, stride 16); same attribute name, same parameter names -> checkpoints load
             from . import mil as _mil
-            from .registry import build_head
-            self.mil_head = build_head(dict(mil_head))
+            self.mil_head = _mil.MAEBoxHeadMIL(**{k: v for k, v in mil_head.items() if k != 'type'})
             rex = bbox_roi_extractor if isinstance(bbox_roi_extractor, dict) else {}
             stride = int((rex.get('featmap_strides') or [16])[0])
             rsize = int((rex.get('roi_layer') or {}).get('output_size', self.mil_head.roi_size))

@@ -83,6 +83,7 @@ def _register_all():
     from . import backbone  # noqa: F401
     try:
         from . import head  # noqa: F401
+        from . import mil  # noqa: F401
     except ImportError:
         pass
 
