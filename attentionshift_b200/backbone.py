@@ -69,7 +69,7 @@ class _PointMLP(nn.Module):     # VTD:26-38
         return x
 
 
-@BACKBONES.register_module()
+@BACKBONES.register_module(force=True)       # force: under a real mmdet this replaces the reference class of the same name
 class VisionTransformerDet(nn.Module):
     def __init__(self, img_size, patch_size, embed_dim, in_chans=3, with_fpn=True, frozen_stages=-1,
                  out_indices=[3, 5, 7, 11], use_checkpoint=False, learnable_pos_embed=True, last_feat=False,

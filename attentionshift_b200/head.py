@@ -23,7 +23,7 @@ from . import attention_shift as AS
 from .registry import HEADS
 
 
-@HEADS.register_module(name=['AttnShiftRoIHead', 'StandardRoIHeadMaskPointSampleDeformAttnReppoints'])
+@HEADS.register_module(name=['AttnShiftRoIHead', 'StandardRoIHeadMaskPointSampleDeformAttnReppoints'], force=True)
 class AttnShiftRoIHead(nn.Module):
     def __init__(self, mil_head=None, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None, mask_head=None,
                  shared_head=None, mae_head=None, bbox_rec_head=None, train_cfg=None, test_cfg=None, visualize=False,
