@@ -15,6 +15,7 @@ call sequence on one generator (exact stream parity; needs one image per call an
 ``randperm(n)[:k]`` is evaluated from its first k draws only.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,7 @@ from . import lib as _l
 from . import ops
 
 PATCH = 16
+CAM_BBOX_SCRATCH_BYTES = 1 << 30     # transient connected-components scratch per call (see cam_bbox)
 SEED_LEVELS = 4          # threshold-doubling rounds of the seed sampling answered by one counting pass
 
 
@@ -41,18 +43,43 @@ class StreamRng:
         return torch.randperm(n, generator=self.g)[:k]
 
 
-class KeyedRng:
-    """One torch CPU generator per (image, stage, instance) key.  Same algorithms as torch.randint / torch.randperm
-    (mt19937, ``random() % range``, forward Fisher-Yates) so a reference run seeded with ``seed_for(key)`` right before
-    the corresponding call yields identical indices.  The raw mt19937 outputs of many keys come from one call into the
-    C ABI (``as_mt19937_draws``), which is what lets the batched host code draw for every instance at once."""
+_M64 = (1 << 64) - 1
 
-    def __init__(self, base_seed=0):
+
+def _mix64(x):
+    """splitmix64 finaliser: a bijection of 64-bit integers with full avalanche."""
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+class KeyedRng:
+    """One torch CPU generator per (rank, call, image, stage, instance) key.  Same algorithms as torch.randint /
+    torch.randperm (mt19937, ``random() % range``, forward Fisher-Yates) so a reference run seeded with ``seed_for(key)``
+    right before the corresponding call yields identical indices.  The raw mt19937 outputs of many keys come from one call
+    into the C ABI (``as_mt19937_draws``), which is what lets the batched host code draw for every instance at once.
+
+    ``step`` advances once per ``seed_pseudo_gt`` / ``update_fg_map`` call (``next_step``, called by the head) and ``rank``
+    defaults to the process's RANK, so -- like the reference's advancing global generator -- no two training iterations and
+    no two DDP ranks draw the same seed points / mask points.  The key is hashed through a 64-bit mixer: slots cannot collide
+    the way a linear ``stage * 101 + obj`` formula does once an image has more than 100 instances."""
+
+    def __init__(self, base_seed=0, rank=None):
         self.base = int(base_seed)
+        self.rank = int(os.environ.get('RANK', 0) or 0) if rank is None else int(rank)
+        self.step = 0
+
+    def next_step(self):
+        self.step += 1
+        return self.step
 
     def seed_for(self, key):
         img, stage, obj = key
-        return (self.base * 1000003 + img * 10007 + stage * 101 + obj) & 0x7fffffff
+        h = _mix64(self.base & _M64)
+        for v in (self.rank, self.step, img, stage, obj):
+            h = _mix64(h ^ (int(v) & _M64))
+        return h & 0x7fffffff
 
     def draws(self, keys, k):
         """Raw 32-bit generator outputs: uint32 array [len(keys), k] (k <= 624)."""
@@ -266,16 +293,23 @@ def rollout_rows(attns, n_rows, use_tensor_cores=True):
     by the head-mean kernel (``_as_t16``) the products run on the tensor cores; otherwise on the fp32 CUDA-core slab GEMM."""
     L = _l.load()
     nl = len(attns)
-    B, T, _ = attns[0].shape
-    ld = attns[0].stride(1)
-    dev = attns[0].device
+    # maps produced for the roll-out only (backbone attn_format='rollout') are empty placeholders that carry the operands as
+    # attributes; the LAST layer's map is always a real tensor (its last n_rows rows are read)
+    B, T, _ = attns[-1].shape
+    ld = attns[-1].stride(1)
+    dev = attns[-1].device
+    if getattr(attns[-1], '_as_valid_from', 0) > T - n_rows:
+        raise ValueError('the last layer\'s head-mean map does not hold the rows the roll-out reads')
     parts = []
     for a in attns:
-        assert a.dtype == torch.float32 and a.stride(2) == 1 and a.stride(1) == ld and a.stride(0) == T * ld
         p = getattr(a, '_as_rowsum_part', None)
+        if a.numel() == 0:
+            assert p is not None and getattr(a, '_as_t16', None) is not None and a._as_shape[:2] == (B, T)
+        else:
+            assert a.dtype == torch.float32 and a.stride(2) == 1 and a.stride(1) == ld and a.stride(0) == T * ld
         parts.append(p if p is not None else a.sum(-1, keepdim=True).contiguous())
     ntile = parts[0].shape[2]
-    a_ptrs = (ctypes.c_void_p * nl)(*[a.data_ptr() for a in attns])
+    a_ptrs = (ctypes.c_void_p * nl)(*[(a if a.numel() else attns[-1]).data_ptr() for a in attns])
     p_ptrs = (ctypes.c_void_p * nl)(*[p.data_ptr() for p in parts])
     t16 = [getattr(a, '_as_t16', None) for a in attns]
     if use_tensor_cores and all(t is not None for t in t16[:-1]) and n_rows <= 128:
@@ -289,6 +323,8 @@ def rollout_rows(attns, n_rows, use_tensor_cores=True):
         _l.check(L.as_rollout_rows_tc(a_ptrs, h_ptrs, l_ptrs, p_ptrs, nl, B, T, ld, ldt, ops.T_SCALE, ntile, n_rows, _p(out),
                                       _p(ws), nbytes, _sp()), 'as_rollout_rows_tc')
         return out[..., :T]
+    if any(a.numel() == 0 for a in attns):
+        raise ValueError('roll-out-only head-mean maps need the tensor-core roll-out (n_rows <= 128)')
     out = torch.empty(B, nl, n_rows, T, device=dev, dtype=torch.float32)
     nbytes = L.as_rollout_workspace(B, T, n_rows)
     ws = _ws(nbytes, dev)
@@ -324,10 +360,20 @@ def cam_bbox(cams, mm, gt_points, hp, wp, cam_thr=0.2, area_ratio=0.5, want_keep
     n_maps = nl * n_tot
     boxes = torch.empty(n_maps, 4, device=dev, dtype=torch.float32)
     keep = torch.empty(n_maps, hp * 16, wp * 16, device=dev, dtype=torch.uint8) if want_keep_mask else None
-    nbytes = L.as_cam_bbox_workspace(n_maps, hp * 16, wp * 16)
+    # scratch is sized for the worst case of H * ceil(W / 2) runs per map (7.3 MB per 1024^2 map): bound it by walking the maps in
+    # groups of whole layers (the kernels are per-map, the [layer][instance] order makes every group a contiguous slice), so a
+    # crowded batch costs a few more launches instead of gigabytes of transient memory
+    per_layer = L.as_cam_bbox_workspace(n_tot, hp * 16, wp * 16)
+    step = max(1, min(nl, CAM_BBOX_SCRATCH_BYTES // max(per_layer, 1)))
+    nbytes = L.as_cam_bbox_workspace(step * n_tot, hp * 16, wp * 16)
     ws = _ws(nbytes, dev)
-    _l.check(L.as_cam_bbox(_p(cams), _p(mm), _p(gt_points), n_maps, n_tot, hp, wp, float(cam_thr), float(area_ratio),
-                           _p(boxes), _p(keep), _p(ws), nbytes, _sp()), 'as_cam_bbox')
+    mm2 = mm.reshape(n_maps, 2)
+    for l0 in range(0, nl, step):
+        l1 = min(nl, l0 + step)
+        m0, m1 = l0 * n_tot, l1 * n_tot
+        _l.check(L.as_cam_bbox(_p(cams[l0:l1]), _p(mm2[m0:m1]), _p(gt_points), m1 - m0, n_tot, hp, wp, float(cam_thr),
+                               float(area_ratio), _p(boxes[m0:m1]), _p(keep[m0:m1]) if keep is not None else None, _p(ws), nbytes,
+                               _sp()), 'as_cam_bbox')
     return boxes.view(nl, n_tot, 4), keep
 
 

@@ -69,14 +69,13 @@ class _PointMLP(nn.Module):     # VTD:26-38
         return x
 
 
-@BACKBONES.register_module(force=True)       # force: under a real mmdet this replaces the reference class of the same name
 class VisionTransformerDet(nn.Module):
     def __init__(self, img_size, patch_size, embed_dim, in_chans=3, with_fpn=True, frozen_stages=-1,
                  out_indices=[3, 5, 7, 11], use_checkpoint=False, learnable_pos_embed=True, last_feat=False,
                  recompute_last_feat=False, point_tokens_num=100, num_classes=20, return_attention=False,
                  with_point_head=True, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=None, init_values=0,
-                 attn_layers=None, cuda_graph=False, **kwargs):
+                 attn_layers=None, attn_format='full', cuda_graph=False, allow_detached_training=False, **kwargs):
         super().__init__()
         assert not with_fpn or (patch_size in (8, 16))
         assert not recompute_last_feat or (last_feat and recompute_last_feat)
@@ -105,11 +104,19 @@ class VisionTransformerDet(nn.Module):
         # which layers emit their head-mean attention map; None = all (reference behaviour, VTD:236/242).
         # The attention-shift head only reads the last ``cam_layer`` = 7 (RH:2261): pass attn_layers=7 to skip the rest.
         self.attn_layers = attn_layers
+        # 'full' (reference behaviour): every emitted map is the fp32 [B,T,T] tensor of VTD:236.  'rollout': produce only what
+        # attention_shift.rollout_rows consumes -- the transposed split-fp16 operand + row sums of every layer but the last, and
+        # the point-token rows of the last one (RH:1265, RH:2272); ``attns`` then holds placeholders / a partially written map and
+        # must not be read as attention maps.  Halves the head-mean pass's output traffic and skips 1/7 of its tiles.
+        if attn_format not in ('full', 'rollout'):
+            raise ValueError("attn_format must be 'full' or 'rollout'")
+        self.attn_format = attn_format
         # replay the whole forward as ONE CUDA graph (static shapes, no host synchronisation inside): the ~200 launches of a
         # step cost the host one call, and every buffer of the forward lives in the graph's private pool.  The returned
         # tensors are views of that pool -- valid until the next forward of the same input shape overwrites them.
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
+        self.allow_detached_training = bool(allow_detached_training)
 
         self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
         num_patches = self.patch_embed.num_patches
@@ -216,7 +223,7 @@ class VisionTransformerDet(nn.Module):
         ptok = (self.point_token + self.point_pos_embed).detach()[0].float().contiguous()
         return ops.assemble_tokens(emb, self.cls_token.detach().reshape(C).float().contiguous(), pos, ptok, B, N)
 
-    def _block(self, i, x, B, T, want_attn):
+    def _block(self, i, x, B, T, want_attn, last_attn=False):
         """VT:109-124 on the device kernels.  x [B*T,C] fp32 (residual stream) -> (x, head-mean attention or None)."""
         blk = self.blocks[i]
         h = self.num_heads
@@ -227,7 +234,12 @@ class VisionTransformerDet(nn.Module):
                                 B, T, h, Tpad)
         o, m, l = ops.mhsa_fwd(q, k, vt, T)
         attn = None
-        if want_attn:
+        if want_attn and self.attn_format == 'rollout':
+            if last_attn:       # only the point-token rows enter the roll-out
+                attn, self._rowsum_part = ops.attn_headmean(q, k, m, l, T, want_transposed=False, row0=T - self.point_tokens_num)
+            else:               # only the GEMM operand + row sums
+                attn, self._rowsum_part = ops.attn_headmean(q, k, m, l, T, want_map=False)
+        elif want_attn:
             attn, self._rowsum_part = ops.attn_headmean(q, k, m, l, T)
         x = ops.linear_f16(o.view(B * T, -1), self._half(f'proj{i}', blk.attn.proj.weight), blk.attn.proj.bias.detach(),
                            ops.EPI_RESID_F32, resid=x)
@@ -240,8 +252,24 @@ class VisionTransformerDet(nn.Module):
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    @torch.no_grad()
+    def _check_no_training(self):
+        """The device path is a forward pass without a backward (attention-shift consumes detached tensors, DET:77).  Called
+        in training mode with autograd on and trainable parameters it would silently return constants to the optimiser -- the
+        backbone would never train and the point losses would have no gradient path -- so it refuses instead."""
+        if self.training and torch.is_grad_enabled() and not self.allow_detached_training and \
+                any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError(
+                'attentionshift_b200.VisionTransformerDet is forward-only (no backward kernels): it cannot train its parameters. '
+                'Use it under torch.no_grad() / .eval() (pseudo-label generation, inference), freeze it (frozen_stages, '
+                'requires_grad_(False)), keep the reference backbone for the trained copy, or pass allow_detached_training=True '
+                'to accept outputs that are detached from the parameters.')
+
     def forward(self, x):           # VTD:221-275
+        self._check_no_training()
+        return self._forward_no_grad(x)
+
+    @torch.no_grad()
+    def _forward_no_grad(self, x):
         if not (self.cuda_graph and x.is_cuda):
             return self._forward_eager(x)
         key = (tuple(x.shape), x.dtype, x.device)
@@ -279,7 +307,7 @@ class VisionTransformerDet(nn.Module):
         Tp = self.point_tokens_num
         for i in range(depth):
             want = self.return_attention and i >= first_attn
-            xs, a = self._block(i, xs, B, T, want)
+            xs, a = self._block(i, xs, B, T, want, last_attn=(i == depth - 1))
             if self.return_attention:
                 attns.append(a)
             if i in self.out_indices:
@@ -303,3 +331,24 @@ class VisionTransformerDet(nn.Module):
         if self.last_feat:
             ret.update(dict(last_feat=last_feat))
         return ret
+
+
+REFERENCE_NAME = 'VisionTransformerDet'
+
+
+def take_over_reference_name():
+    """Explicit opt-in for a real mmdet tree: make ``type='VisionTransformerDet'`` in configs/mae build THIS class instead of the
+    reference's (registry ``force=True``).  Only for runs that do not train the backbone -- see ``_check_no_training``."""
+    BACKBONES.register_module(name=REFERENCE_NAME, force=True, module=VisionTransformerDet)
+
+
+def _register():
+    """Always registered as ``VisionTransformerDetB200``.  The reference's name is taken only where no reference class exists
+    (this repo's shim registry, or an mmdet without the AttentionShift backbone); inside the reference tree the reference class
+    keeps it until ``take_over_reference_name()`` is called (forward-only path: it must not silently replace a trained module)."""
+    BACKBONES.register_module(name='VisionTransformerDetB200', force=True, module=VisionTransformerDet)
+    if BACKBONES.get(REFERENCE_NAME) is None:
+        BACKBONES.register_module(name=REFERENCE_NAME, module=VisionTransformerDet)
+
+
+_register()

@@ -127,6 +127,37 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// ---------------------------------------------------------------- L2 cache policies
+// createpolicy descriptors for loads that should stay in L2 (operands re-read by many CTAs) and for streaming stores that
+// should leave it first (outputs nobody reads again inside the kernel)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_f4_hint(float* ptr, float4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_u4_hint(void* ptr, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(policy)
+               : "memory");
+}
+
 // multicast variant: the box lands at the same CTA-relative smem offset of every CTA in cta_mask and performs
 // complete_tx on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,

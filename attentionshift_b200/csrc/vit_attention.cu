@@ -625,6 +625,7 @@ struct HmParams {
   __half* t_lo;
   int ldt;
   float t_scale;
+  int qt0, nqt;               // query tiles [qt0, qt0 + nqt) are produced (persistent schedule only); default: all
 };
 
 __global__ void __launch_bounds__(HM_THREADS, 1)
@@ -810,14 +811,16 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) {
     if (elect_one()) {
       uint32_t g = 0;
+      // every (q-tile, k-tile) re-reads the Q / K tiles of all heads: keep them in L2 against the output streams
+      const uint64_t keep = l2_policy_evict_last();
       for (int tile = tile0; tile < tile1; ++tile) {
-        const int b = tile / (nt * nt), r = tile - b * nt * nt, qt = r / nt, kt = r - qt * nt;
+        const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
         for (int h = 0; h < p.heads; ++h, ++g) {
           const uint32_t st = g % HM2_STAGES;
           mbar_wait(&empty[st], ((g / HM2_STAGES) & 1) ^ 1);
           mbar_expect_tx(&full[st], 2 * TILE_BYTES);
-          tma_load_3d(smem + (2 * st) * TILE_BYTES, &tm_q, &full[st], 0, qt * BQ, b * p.heads + h);
-          tma_load_3d(smem + (2 * st + 1) * TILE_BYTES, &tm_k, &full[st], 0, kt * BKV, b * p.heads + h);
+          tma_load_3d_hint(smem + (2 * st) * TILE_BYTES, &tm_q, &full[st], 0, qt * BQ, b * p.heads + h, keep);
+          tma_load_3d_hint(smem + (2 * st + 1) * TILE_BYTES, &tm_k, &full[st], 0, kt * BKV, b * p.heads + h, keep);
         }
       }
     }
@@ -847,8 +850,9 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const float inv_h = 1.f / (float)p.heads;
     uint32_t g = 0;
     int cur_bq = -1;
+    const uint64_t stream_out = l2_policy_evict_first();   // the maps are written once and read by a later kernel
     for (int tile = tile0; tile < tile1; ++tile) {
-      const int b = tile / (nt * nt), r = tile - b * nt * nt, qt = r / nt, kt = r - qt * nt;
+      const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
       const int t = qt * BQ + row;
       if (b * nt + qt != cur_bq) {                     // new query tile: softmax row statistics of all heads -> smem
         cur_bq = b * nt + qt;
@@ -904,14 +908,14 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
       if (t < p.T && p.rowsum_part) p.rowsum_part[((size_t)b * p.T + t) * (4 * nt) + kt * 4 + cslice] = rs;
       __syncwarp();
-      {
+      if (p.out) {
         const int rr = lane >> 3, cc = (lane & 7) * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r2 = it * 4 + rr, t2 = qt * BQ + quad * 32 + r2;
           const float* sp = st + r2 * 33 + cc;
           const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-          if (t2 < p.T) *reinterpret_cast<float4*>(p.out + ((size_t)b * p.T + t2) * p.ld + c0 + cc) = v;
+          if (t2 < p.T) st_global_f4_hint(p.out + ((size_t)b * p.T + t2) * p.ld + c0 + cc, v, stream_out);
         }
       }
       if (p.t_hi) {
@@ -932,8 +936,8 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             lw[e] = *reinterpret_cast<const uint32_t*>(&lo);
           }
           const size_t o = ((size_t)b * p.ldt + c0 + col) * p.ldt + qt * BQ + quad * 32 + r0;
-          *reinterpret_cast<uint4*>(p.t_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(p.t_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          st_global_u4_hint(p.t_hi + o, make_uint4(hw[0], hw[1], hw[2], hw[3]), stream_out);
+          st_global_u4_hint(p.t_lo + o, make_uint4(lw[0], lw[1], lw[2], lw[3]), stream_out);
         }
       }
     }
@@ -1012,11 +1016,18 @@ extern "C" int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o
 
 // out [B,T,ld] fp32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] (may be null).  rowsum_slices selects the
 // schedule: 4 = persistent kernel (one row-sum partial per 32-column slice), 1 = first-generation kernel (one per tile).
-extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
-                                float* rowsum_part, int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B,
-                                int T, int heads, cudaStream_t stream) {
-  if (ld < T || heads > HM_MAX_HEADS) return AS_ERR_BAD_ARG;
+// Persistent schedule only: ``out`` may be null (only the transposed split-fp16 pair and the row sums are produced -- all the
+// roll-out reads of a layer that is not the last, RH:1265), and ``q_row0`` > 0 restricts the work to the query tiles that
+// contain rows [q_row0, T) (the roll-out reads only the point-token rows of the LAST layer, RH:2272); rows of ``out`` /
+// ``rowsum_part`` before the first such tile are not written.
+extern "C" int as_attn_headmean_ex(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
+                                   float* rowsum_part, int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B,
+                                   int T, int heads, int q_row0, cudaStream_t stream) {
+  if (ld < T || heads > HM_MAX_HEADS || q_row0 < 0 || q_row0 >= T) return AS_ERR_BAD_ARG;
   if (t_hi && (!t_lo || ldt != (T + BKV - 1) / BKV * BKV)) return AS_ERR_BAD_ARG;
+  if (!out && !t_hi) return AS_ERR_BAD_ARG;
+  if ((!out || q_row0 > 0) && rowsum_slices != 4) return AS_ERR_BAD_ARG;
+  if (q_row0 > 0 && t_hi) return AS_ERR_BAD_ARG;            // the transposed copy must be complete: it is a GEMM operand
   CUtensorMap tm_q, tm_k;
   int r = encode_qk(&tm_q, q, B * heads, T);
   if (r) return r;
@@ -1037,9 +1048,10 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
   p.m = m; p.l = l; p.out = out; p.rowsum_part = rowsum_part; p.ntile = (T + BKV - 1) / BKV;
   p.t_hi = (__half*)t_hi; p.t_lo = (__half*)t_lo; p.ldt = ldt; p.t_scale = t_scale;
   const int nt = (T + BQ - 1) / BQ;
+  p.qt0 = q_row0 / BQ; p.nqt = nt - p.qt0;
   if (rowsum_slices == 4) {
     if (ld % 4 || ld < nt * BKV) return AS_ERR_BAD_ARG;   // float4 row stores, whole 128-column tiles
-    const int n_tiles = nt * nt * B;
+    const int n_tiles = p.nqt * nt * B;
     const int per = (n_tiles + num_sms - 1) / num_sms;
     const int grid = (n_tiles + per - 1) / per;
     attn_headmean2_kernel<<<grid, HM_THREADS, HM2_SMEM, stream>>>(tm_q, tm_k, p, n_tiles, per);
@@ -1050,4 +1062,11 @@ extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, co
   }
   AS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld,
+                                float* rowsum_part, int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B,
+                                int T, int heads, cudaStream_t stream) {
+  if (!out) return AS_ERR_BAD_ARG;
+  return as_attn_headmean_ex(q, k, m, l, out, ld, rowsum_part, rowsum_slices, t_hi, t_lo, ldt, t_scale, B, T, heads, 0, stream);
 }

@@ -23,8 +23,12 @@ from . import attention_shift as AS
 from .registry import HEADS
 
 
-@HEADS.register_module(name=['AttnShiftRoIHead', 'StandardRoIHeadMaskPointSampleDeformAttnReppoints'], force=True)
 class AttnShiftRoIHead(nn.Module):
+    """The attention-shift half of the reference RoI head (``seed_pseudo_gt`` RH:2209-2415, ``update_fg_map`` RH:2737-2760).
+    It does NOT implement the loss side (``forward_train`` / ``simple_test`` / ``init_weights`` / bbox and mask heads), so it
+    never takes the reference class's registry names inside a real mmdet: see ``_register`` at the bottom of this module and
+    ``attach`` / ``make_dropin`` for how it is combined with the reference head there."""
+
     def __init__(self, mil_head=None, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None, mask_head=None,
                  shared_head=None, mae_head=None, bbox_rec_head=None, train_cfg=None, test_cfg=None, visualize=False,
                  epoch=0, epoch_semantic_centers=0, num_semantic_points=3, semantic_to_token=False, pca_dim=128,
@@ -61,9 +65,11 @@ class AttnShiftRoIHead(nn.Module):
             rex = bbox_roi_extractor if isinstance(bbox_roi_extractor, dict) else {}
             stride = int((rex.get('featmap_strides') or [16])[0])
             rsize = int((rex.get('roi_layer') or {}).get('output_size', self.mil_head.roi_size))
-            self.mil_fn = lambda boxes, labels, fmap, metas: _mil.mil_select(self.mil_head, fmap, boxes, labels, stride, rsize)
-        self.rng = rng if rng is not None else AS.KeyedRng(0)
-        self.with_mil = mil_head is not None or mil_fn is not None
+            self._mil_stride, self._mil_rsize = stride, rsize          # mil_fn stays None: _mil_select dispatches to self.mil_head
+        # default RNG: keyed off torch's seed and the rank, advanced once per call (the reference draws from the advancing global
+        # generator: different seed / mask points every iteration and on every rank)
+        self.rng = rng if rng is not None else AS.KeyedRng(torch.initial_seed() & 0x7fffffff)
+        self.with_mil = mil_head is not None or mil_fn is not None or hasattr(self, 'mil_head')
         self.with_deform_sup = False
         self._mask_bufs = {}
 
@@ -102,7 +108,11 @@ class AttnShiftRoIHead(nn.Module):
         ``(index, losses)``, or the reference's ``_mil_forward_train(..., return_index=True)`` triple
         ``(boxes, losses, index)`` -- see ``mil_from_reference``.  -> (gt_index [n_tot] long on the device, losses dict)."""
         per_img = list(boxes.permute(1, 0, 2).split(list(n_per_img), dim=0))
-        out = self.mil_fn(per_img, gt_labels, roi_feature_map, img_metas)
+        if self.mil_fn is not None:
+            out = self.mil_fn(per_img, gt_labels, roi_feature_map, img_metas)
+        else:                                   # own MIL head (a bound dispatch: survives deepcopy / pickling of the module)
+            from . import mil as _mil
+            out = _mil.mil_select(self.mil_head, roi_feature_map, per_img, gt_labels, self._mil_stride, self._mil_rsize)
         losses = {}
         if isinstance(out, tuple) and len(out) == 3:
             _, losses, idx = out
@@ -123,6 +133,8 @@ class AttnShiftRoIHead(nn.Module):
         [B,1+N,C] (cls token first); semantic_centers_coords: list of [P_i,2]; obj_num_parts: list of lists; inst_fg_feat /
         inst_bg_feat: the ``seed_pseudo_gt`` outputs; gt_bboxes: list of [n_i,4].
         -> (list of [n_i,H,W] maps on the device, list of uint8 numpy masks)."""
+        if hasattr(self.rng, 'next_step'):
+            self.rng.next_step()
         n_per_img = [int(m.shape[0]) for m in map_cos_fg]
         H, W = map_cos_fg[0].shape[-2:]
         hp, wp = H // 16, W // 16
@@ -141,6 +153,8 @@ class AttnShiftRoIHead(nn.Module):
                        attns=None, gt_points=None, gt_points_labels=None, roi_feature_map=None, return_mask=False,
                        pos_mask_thr=0.6, neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, point_adjuster=None,
                        edges=None, obj_tau=0.85, pos_inds=None, gt_index=None):
+        if hasattr(self.rng, 'next_step'):
+            self.rng.next_step()                # a new set of random draws per call (and per rank), like the reference's stream
         feats = AS.token_major(vit_feat)
         if vit_feat.dim() == 4:
             hp, wp = vit_feat.shape[-2:]
@@ -187,7 +201,7 @@ class AttnShiftRoIHead(nn.Module):
             begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
         boxes, _ = AS.cam_bbox(cams, mm, pts, hp, wp, self.seed_thr, self.seed_multiple)
         if gt_index is None:
-            if self.mil_fn is None:
+            if self.mil_fn is None and not hasattr(self, 'mil_head'):
                 raise ValueError('seed_pseudo_gt needs gt_index= or a mil_fn (MIL head is outside the hot path)')
             gt_index, mil_losses = self._mil_select(boxes, n_per_img, labels, roi_feature_map, img_metas)
             begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
@@ -247,3 +261,55 @@ def mil_from_reference(ref_head):
     def fn(boxes_per_img, gt_labels, roi_feature_map, img_metas):
         return ref_head._mil_forward_train(roi_feature_map, None, boxes_per_img, gt_labels, img_metas, return_index=True)
     return fn
+
+
+REFERENCE_NAMES = ('AttnShiftRoIHead', 'StandardRoIHeadMaskPointSampleDeformAttnReppoints')
+
+
+def attach(ref_head, **fast_kwargs):
+    """Give an INSTANCE of the reference RoI head this repo's device path: ``seed_pseudo_gt`` and ``update_fg_map`` are replaced,
+    everything else (losses, test-time methods, sub-heads, ``init_weights``) stays the reference's.  The fast head reads its
+    knobs off the reference instance and defers the MIL stage to the reference's own ``_mil_forward_train``."""
+    kw = dict(bbox_head=dict(cam_layer=getattr(getattr(ref_head, 'bbox_head', None), 'cam_layer', 7),
+                             seed_thr=getattr(getattr(ref_head, 'bbox_head', None), 'seed_thr', 0.2),
+                             seed_multiple=getattr(getattr(ref_head, 'bbox_head', None), 'seed_multiple', 0.5)),
+              train_cfg=getattr(ref_head, 'train_cfg', None), num_semantic_points=getattr(ref_head, 'num_semantic_points', 3),
+              mean_shift_times_local=getattr(ref_head, 'mean_shift_times_local', 10),
+              mil_fn=mil_from_reference(ref_head) if hasattr(ref_head, '_mil_forward_train') else None)
+    kw.update(fast_kwargs)
+    fast = AttnShiftRoIHead(**kw)
+    object.__setattr__(ref_head, '_as_b200', fast)          # not a registered submodule: it owns no parameters
+    ref_head.seed_pseudo_gt = fast.seed_pseudo_gt
+    ref_head.update_fg_map = fast.update_fg_map
+    return ref_head
+
+
+def make_dropin(ref_cls):
+    """Class-level version of ``attach`` for the registry: a subclass of the reference head whose constructor runs the
+    reference's and then swaps in the device path.  ``HEADS.register_module(name='AttnShiftRoIHead', module=make_dropin(Ref))``
+    makes configs/mae build the full head (losses included) with the fast ``seed_pseudo_gt``."""
+    class AttnShiftRoIHeadDropIn(ref_cls):
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            attach(self)
+    AttnShiftRoIHeadDropIn.__name__ = 'AttnShiftRoIHead'
+    return AttnShiftRoIHeadDropIn
+
+
+def _register():
+    """Registry policy (mmdet/models/builder.py:6-12).  Always: ``AttnShiftRoIHeadB200`` = this module's class.  Without mmdet
+    (the shim registry of this repo) there is no reference head, so the reference's two names build it as well.  Inside a
+    real mmdet the reference class keeps its name; the config's ``AttnShiftRoIHead`` (which the reference itself never
+    registers -- its rename is incomplete, roi_heads/__init__.py:24) becomes the reference class + device path when the
+    reference class is there, and is left alone otherwise."""
+    from .registry import USING_MMDET
+    HEADS.register_module(name='AttnShiftRoIHeadB200', force=True, module=AttnShiftRoIHead)
+    if not USING_MMDET:
+        HEADS.register_module(name=list(REFERENCE_NAMES), force=True, module=AttnShiftRoIHead)
+        return
+    ref = HEADS.get(REFERENCE_NAMES[1])                     # pragma: no cover - needs mmdet
+    if ref is not None and HEADS.get(REFERENCE_NAMES[0]) is None:
+        HEADS.register_module(name=REFERENCE_NAMES[0], module=make_dropin(ref))
+
+
+_register()

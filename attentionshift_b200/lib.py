@@ -29,6 +29,7 @@ SIGNATURES = {
     'as_timer_record': (_i, [_i, _i, _vp]),
     'as_timer_elapsed': (_i, [_i, _vp]),
     'as_attn_headmean': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
+    'as_attn_headmean_ex': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
     'as_bgemm_f16_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _f, _vp]),
     'as_rollout_tc_workspace': (_sz, [_i, _i, _i]),
     'as_rollout_rows_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _sz, _vp]),
@@ -40,6 +41,10 @@ SIGNATURES = {
     'as_mean_shift_fused_workspace': (_sz, [_i, _i, _i]),
     'as_mean_shift_fused_debug': (None, [_vp]),
     'as_mean_shift_fused': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
+    'as_mean_shift_v2_supported': (_i, [_i, _i, _i, _i]),
+    'as_mean_shift_v2_workspace': (_sz, [_i, _i, _i, _i, _i]),
+    'as_mean_shift_v2_debug': (None, [_vp]),
+    'as_mean_shift_v2': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'as_rollout_workspace': (_sz, [_i, _i, _i]),
@@ -157,7 +162,7 @@ def load():
             fn = getattr(cdll, name)            # AttributeError here = header / library drift
             fn.restype = res
             fn.argtypes = args
-            setattr(lib, name, fn if name.endswith('_workspace') else TIMERS.wrap(name, fn))
+            setattr(lib, name, fn if name.endswith(('_workspace', '_supported', '_debug')) else TIMERS.wrap(name, fn))
         _lib = lib
     return _lib
 

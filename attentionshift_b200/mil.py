@@ -21,6 +21,7 @@ class MAEBoxHeadMIL(nn.Module):
                  use_checkpoint=False, num_layers_query=12, loss_mil_factor=1.0, hidden_dim=1024, roi_size=7, num_classes=80,
                  **kwargs):
         super().__init__()
+        self.pretrained = pretrained
         self.num_classes = num_classes
         self.num_layers_query = num_layers_query
         self.loss_mil_factor = loss_mil_factor
@@ -34,6 +35,32 @@ class MAEBoxHeadMIL(nn.Module):
         self.fc2 = nn.Linear(hidden_dim, hidden_dim)
         self.proposal_branch = nn.Linear(hidden_dim, num_classes)
         self.classification_branch = nn.Linear(hidden_dim, num_classes)
+
+    def _init_weights(self, m):                                                   # MIL:63-70
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02, a=-2., b=2.)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def init_weights(self, pretrained=None):                                      # MIL:72-101
+        """Reference initialisation: trunc_normal(0.02) Linear weights, zero biases, unit LayerNorm -- or, when the head was
+        built with ``pretrained=True`` and a checkpoint path is given, that checkpoint minus the encoder's entries.  (The
+        reference's ``pretrained is None`` branch also touches a ``det_token`` that its constructor never creates.)"""
+        if self.pretrained and isinstance(pretrained, str):
+            import os
+            if not os.path.isfile(pretrained):
+                raise ValueError(f'checkpoint path {pretrained} is invalid')
+            ckpt = torch.load(pretrained, map_location='cpu')
+            sd = ckpt.get('state_dict', ckpt.get('model', ckpt))
+            sd = {k: v for k, v in sd.items() if not (k.startswith('patch_embed') or k.startswith('blocks') or k == 'pos_embed')}
+            self.load_state_dict(sd, strict=False)
+        elif pretrained is None or isinstance(pretrained, str):
+            self.apply(self._init_weights)
+        else:
+            raise TypeError('pretrained must be a str or None')
 
     def mil_losses(self, cls_score, labels):                                      # MIL:134-138
         cls_score = cls_score.clamp(1e-6, 1 - 1e-6)

@@ -89,24 +89,38 @@ T_SCALE = 16384.0     # 2^14: head-mean probabilities (<= 1) as split fp16 witho
 HEADMEAN_SLICES = 1 if os.environ.get('AS_HEADMEAN_VARIANT', '2') == '1' else 4
 
 
-def attn_headmean(q, k, m, l, T, want_rowsum=True, want_transposed=True, slices=None):
+def attn_headmean(q, k, m, l, T, want_rowsum=True, want_transposed=True, slices=None, want_map=True, row0=0):
     """VTD:236/242 attn.mean(1) recomputed from (q, k, m, l).  -> mean [B,T,T] (view of a row-padded buffer).  The
     tensor carries what the roll-out slab needs as attributes: ``_as_rowsum_part`` [B,T,slices*ceil(T/128)] and, when
     ``want_transposed``, ``_as_t16`` = (hi, lo) split-fp16 transposed maps [B,Tpad,Tpad] scaled by T_SCALE.
-    ``slices`` = 4 (default): persistent kernel; 1: one CTA per tile (env AS_HEADMEAN_VARIANT=1)."""
+    ``slices`` = 4 (default): persistent kernel; 1: one CTA per tile (env AS_HEADMEAN_VARIANT=1).
+    Roll-out-only production (persistent kernel): ``want_map=False`` skips the fp32 map (the returned tensor is an EMPTY
+    placeholder that only carries the attributes plus ``_as_shape`` = (B, T, ld)); ``row0`` > 0 computes only the query tiles
+    holding rows [row0, T) -- the rest of the returned map is uninitialised memory (``_as_valid_from`` = first valid row)."""
     L = _l.load()
     slices = HEADMEAN_SLICES if slices is None else slices
     B, heads = q.shape[0], q.shape[1]
     ld = (T + 127) // 128 * 128
-    buf = torch.empty(B, T, ld, device=q.device, dtype=torch.float32)
     nt = (T + 127) // 128
+    lean = (not want_map) or row0 > 0
+    if lean and slices != 4:
+        raise ValueError('roll-out-only head-mean production needs the persistent schedule (slices=4)')
+    if row0 > 0 and want_transposed:
+        raise ValueError('row0 > 0 produces a partial map: it cannot come with the transposed GEMM operand')
+    buf = torch.empty(B, T, ld, device=q.device, dtype=torch.float32) if want_map else None
     part = torch.empty(B, T, slices * nt, device=q.device, dtype=torch.float32) if want_rowsum else None
     thi = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
     tlo = torch.empty(B, ld, ld, device=q.device, dtype=torch.float16) if want_transposed else None
-    _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), slices, _l.ptr(thi),
-                                _l.ptr(tlo), ld, T_SCALE, B, T, heads, _l.stream_ptr()), 'as_attn_headmean')
-    out = buf[:, :, :T]
+    if lean:
+        _l.check(L.as_attn_headmean_ex(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), slices, _l.ptr(thi),
+                                       _l.ptr(tlo), ld, T_SCALE, B, T, heads, int(row0), _l.stream_ptr()), 'as_attn_headmean_ex')
+    else:
+        _l.check(L.as_attn_headmean(_l.ptr(q), _l.ptr(k), _l.ptr(m), _l.ptr(l), _l.ptr(buf), ld, _l.ptr(part), slices, _l.ptr(thi),
+                                    _l.ptr(tlo), ld, T_SCALE, B, T, heads, _l.stream_ptr()), 'as_attn_headmean')
+    out = buf[:, :, :T] if want_map else torch.empty(0, device=q.device, dtype=torch.float32)
     out._as_rowsum_part = part
+    out._as_shape = (B, T, ld)
+    out._as_valid_from = (int(row0) // 128) * 128
     if want_transposed:
         out._as_t16 = (thi, tlo)
     return out, part
@@ -169,8 +183,9 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
                n_per_img=None, use_tensor_cores=True, impl=None):
     """RH:830-854 + RH:882-908 on device.  proto [n_tot,S,C] (consumed), feats [n_img,N,C]; instances grouped by image.
     -> (proto [n_tot,S,C], sim [n_tot,S,N], trace [n_shift,n_tot,N] int32 or None).
-    impl: 'fused' (one persistent cooperative kernel; C % 128 == 0, C <= 768, <= 64 seed columns per image), 'tc' (batched split-fp16
-    affinity GEMM + small kernels), 'fp32' (CUDA-core kernels, any C); None picks the first that fits."""
+    impl: 'v2' (one persistent cooperative kernel, two CTAs per SM; C % 128 == 0, <= 256 seed columns and <= 16 instances per
+    image), 'fused' (the round-1 persistent kernel: C <= 768, <= 64 seed columns, <= 8 instances), 'tc' (batched split-fp16 affinity
+    GEMM + small kernels), 'fp32' (CUDA-core kernels, any C); None picks the first that fits."""
     L = _l.load()
     n_tot, S, C = proto.shape
     n_img, N, _ = feats.shape
@@ -181,15 +196,25 @@ def mean_shift(proto, feats, obj_img, rois, hp, wp, n_shift, tau=0.1, temp=0.1, 
     if n_per_img is None:
         n_per_img = torch.bincount(obj_img.long(), minlength=n_img).cpu().tolist()      # host sync: pass n_per_img to avoid it
     kmax = max(n_per_img) * S
+    max_obj = max(n_per_img)
     if impl is None:
         if not use_tensor_cores or C % 64 != 0:
             impl = 'fp32'
-        elif C % 128 == 0 and C <= 768 and kmax <= 64 and max(n_per_img) <= 8 and (N + 255) // 256 <= _num_sms(dev):
-            impl = 'fused'
+        elif L.as_mean_shift_v2_supported(N, C, kmax, max_obj) and S <= 127 and \
+                ((N + 63) // 64 + 1) // 2 <= (2 if kmax <= 64 and max_obj <= 8 else 1) * _num_sms(dev):
+            impl = 'v2'
         elif kmax <= 256 and S * C * 4 <= 200 * 1024:
             impl = 'tc'
         else:
             impl = 'fp32'
+    if impl == 'v2':
+        d_first, d_nobj = _group_index(n_per_img, dev)
+        nbytes = L.as_mean_shift_v2_workspace(n_img, N, C, kmax, max_obj)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _l.check(L.as_mean_shift_v2(ctypes_ptr(feats), _feat_args(feats), n_img, N, C, hp, wp, _l.ptr(d_first), _l.ptr(d_nobj),
+                                    kmax, max_obj, _l.ptr(rois), n_tot, S, _l.ptr(proto), _l.ptr(sim), n_shift, float(tau),
+                                    float(temp), int(clamp0), _l.ptr(trace), _l.ptr(ws), nbytes, _l.stream_ptr()), 'as_mean_shift_v2')
+        return proto, sim, trace
     if impl in ('fused', 'tc'):
         d_first, d_nobj = _group_index(n_per_img, dev)
         if impl == 'fused':

@@ -24,8 +24,23 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name='cfg2: bs8 1024x1024 ViT-B/16, 5 attn-shift iters, 16 seeds/instance', batch=8, img=1024, embed=768,
-                depth=12, heads=12, n_obj=3, iters=5, seeds=16, cam_layer=7, n_point_tokens=100)
+# BASELINE.json configs.  cfg2 is the one the metric is quoted on (default); cfg1 is the reference's own CPU-runnable case,
+# cfg3 the roofline-capture case, cfg4 one rank's share of the 8-GPU DDP case, cfg5 the ViT-L / COCO-shape case (2 per GPU).
+CONFIGS = {
+    'cfg1': dict(name='cfg1: 1x224x224 ViT-B/16, 2 attn-shift iters, 4 seeds/instance', batch=1, img=(224, 224), embed=768, depth=12,
+                 heads=12, n_obj=2, iters=2, seeds=4),
+    'cfg2': dict(name='cfg2: bs8 1024x1024 ViT-B/16, 5 attn-shift iters, 16 seeds/instance', batch=8, img=(1024, 1024), embed=768,
+                 depth=12, heads=12, n_obj=3, iters=5, seeds=16),
+    'cfg3': dict(name='cfg3: bs32 1024x1024 ViT-B/16, 10 attn-shift iters, 32 seeds/instance', batch=32, img=(1024, 1024), embed=768,
+                 depth=12, heads=12, n_obj=3, iters=10, seeds=32),
+    'cfg4': dict(name='cfg4: bs64 over 8 GPUs = bs8 per GPU, 1024x1024 ViT-B/16, 10 attn-shift iters, 16 seeds/instance', batch=8,
+                 img=(1024, 1024), embed=768, depth=12, heads=12, n_obj=3, iters=10, seeds=16),
+    'cfg5': dict(name='cfg5: bs16 over 8 GPUs = bs2 per GPU, 1344x800 (COCO shape, padded) ViT-L/16, 10 attn-shift iters, 64 seeds/instance',
+                 batch=2, img=(800, 1344), embed=1024, depth=24, heads=16, n_obj=3, iters=10, seeds=64),
+}
+for _c in CONFIGS.values():
+    _c.update(cam_layer=7, n_point_tokens=100)
+WORKLOAD = CONFIGS['cfg2']
 
 
 def parse():
@@ -34,7 +49,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-config', action='store_true', help='skip the untouched-reference-config leg (cfg2, N=1)')
     ap.add_argument('--small', action='store_true', help='tiny config for a functional check (not a valid bench number)')
     return ap.parse_args()
 
@@ -136,26 +153,37 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------- ours
-def make_inputs(cfg, rank):
+def make_inputs(cfg, rank, pin=True):
+    """Synthetic batch of the workload: randn images (already normalised), GT points, and the two selections that stand in for
+    the learned / host-side stages: pos_inds for the Hungarian match, gt_index for the MIL layer choice.  The SAME
+    function feeds the CUDA arm and the CPU arm (which runs image 0 of rank 0's batch)."""
     g = torch.Generator().manual_seed(1234 + rank)
-    B, S = cfg['batch'], cfg['img']
-    img = torch.randn(B, 3, S, S, generator=g).pin_memory()
+    B, (H, W) = cfg['batch'], cfg['img']
+    img = torch.randn(B, 3, H, W, generator=g)
+    if pin:
+        img = img.pin_memory()
     n = cfg['n_obj']
-    gt_points = [(torch.rand(n, 2, generator=g) * (S - 200) + 100).floor() for _ in range(B)]
+    span = torch.tensor([W - 0.2 * W, H - 0.2 * H])
+    gt_points = [(torch.rand(n, 2, generator=g) * span + 0.1 * torch.tensor([W, H])).floor() for _ in range(B)]
     pos_inds = [torch.arange(n) for _ in range(B)]                       # stands in for the Hungarian match (SURVEY 8d)
     gt_index = [torch.randint(0, cfg['cam_layer'], (n,), generator=g) for _ in range(B)]    # stands in for the MIL choice
     labels = [torch.randint(0, 20, (n,), generator=g) for _ in range(B)]
     return img, gt_points, pos_inds, gt_index, labels
 
 
-def build_models(cfg, dev):
+def build_models(cfg, dev, reference_config=False):
+    """reference_config=False: the fast drop-in -- head-mean maps only for the 7 layers seed_pseudo_gt reads and only in the form the
+    roll-out consumes, no FPN (outside SURVEY 8a), forward replayed as one CUDA graph.  reference_config=True: the backbone exactly
+    as configs/mae builds it (all 12 full fp32 maps, FPN on, eager launches)."""
     from attentionshift_b200.registry import build_backbone, build_head
     from attentionshift_b200.synthetic import vit_state_dict
-    bb = build_backbone(dict(type='VisionTransformerDet', img_size=cfg['img'], patch_size=16, embed_dim=cfg['embed'],
-                             depth=cfg['depth'], num_heads=cfg['heads'], mlp_ratio=4, qkv_bias=True, with_fpn=False,
-                             last_feat=True, return_attention=True, point_tokens_num=cfg['n_point_tokens'],
-                             attn_layers=cfg['cam_layer'], out_indices=[3, 5, 7, 11], cuda_graph=cfg.get('cuda_graph', True)))
-    sd = vit_state_dict(cfg['embed'], cfg['depth'], cfg['heads'], cfg['img'], n_point_tokens=cfg['n_point_tokens'], seed=0)
+    H, W = cfg['img']
+    kw = dict(with_fpn=True) if reference_config else dict(with_fpn=False, attn_layers=cfg['cam_layer'], attn_format='rollout',
+                                                            cuda_graph=cfg.get('cuda_graph', True))
+    bb = build_backbone(dict(type='VisionTransformerDet', img_size=H if H == W else 224, patch_size=16, embed_dim=cfg['embed'],
+                             depth=cfg['depth'], num_heads=cfg['heads'], mlp_ratio=4, qkv_bias=True, last_feat=True,
+                             return_attention=True, point_tokens_num=cfg['n_point_tokens'], out_indices=[3, 5, 7, 11], **kw))
+    sd = vit_state_dict(cfg['embed'], cfg['depth'], cfg['heads'], H if H == W else 224, n_point_tokens=cfg['n_point_tokens'], seed=0)
     bb.load_state_dict(sd, strict=False)
     bb = bb.to(dev).eval()
     head = build_head(dict(type='AttnShiftRoIHead', bbox_head=dict(cam_layer=cfg['cam_layer'], seed_thr=0.2, seed_multiple=0.5),
@@ -166,14 +194,19 @@ def build_models(cfg, dev):
 def one_step(bb, head, img_dev, inputs, return_mask):
     _, gt_points, pos_inds, gt_index, labels = inputs
     out = bb(img_dev)
-    hp = img_dev.shape[-1] // 16
+    hp, wp = img_dev.shape[-2] // 16, img_dev.shape[-1] // 16
     vit_feat = out['last_feat'][:, 1:]                                   # token-major [B,N,C] view (DET:77 without the transpose)
-    res = head.seed_pseudo_gt(out['feature'], None, None, None, None, vit_feat=vit_feat.unflatten(1, (hp, hp)).permute(0, 3, 1, 2),
+    res = head.seed_pseudo_gt(out['feature'], None, None, None, None, vit_feat=vit_feat.unflatten(1, (hp, wp)).permute(0, 3, 1, 2),
                               point_cls=out['outputs_class'], point_reg=out['outputs_coord'], attns=out['attns'],
                               gt_points=gt_points, gt_points_labels=labels, return_mask=return_mask, pos_mask_thr=0.6,
                               neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, obj_tau=0.85, pos_inds=pos_inds,
                               gt_index=gt_index)
     return res
+
+
+OURS = ('linear_tcgen05', 'mhsa_fwd', 'attn_headmean', 'layernorm_f16', 'im2col16', 'assemble_tokens', 'rollout_', 'cam_', 'ccl_',
+        'ms_', 'mean_shift', 'split_tokens', 'norm_', 'seed_proto', 'refine_', 'weighted_sum', 'cos_warp', 'fuse_', 'crop_', 'erode_down',
+        'filter_score', 'merge_protos', 'part_', 'fill_u32', 'minmax_decode', 'ext_init')
 
 
 def count_launches(fn):
@@ -183,33 +216,41 @@ def count_launches(fn):
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             fn()
             torch.cuda.synchronize()
-        ours = ('linear_tcgen05', 'mhsa_fwd', 'attn_headmean', 'layernorm_f16', 'im2col16', 'assemble_tokens', 'rollout_', 'cam_',
-                'ccl_', 'ms_', 'norm_', 'seed_proto', 'refine_', 'weighted_sum', 'fuse_', 'crop_', 'erode_down', 'filter_score',
-                'merge_protos', 'part_', 'fill_u32', 'minmax_decode', 'ext_init')
         n_ours = n_all = 0
         for e in prof.events():
             if 'cuda' in str(e.device_type).lower() and e.name and not e.name.startswith('Memcpy') and not e.name.startswith('Memset'):
                 n_all += 1
-                if any(k in e.name for k in ours):
+                if any(k in e.name for k in OURS):
                     n_ours += 1
         return n_ours, n_all
     except Exception:
         return None, None
 
 
+def time_steps(fn, steps, barrier):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
 def run_ours(args):
     from attentionshift_b200 import parallel
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
-        os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line the driver parses
+    if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+        os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'   # NCCL's log stays visible (rank / transport checks) without touching stdout's JSON line
     rank, world, local = parallel.env_rank_world()
     # the host side of a rank is one launching thread: keep torch's CPU pool from oversubscribing the box when 8 ranks share it
     torch.set_num_threads(max(1, min(4, usable_cpus() // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     parallel.init('nccl', dev)
-    cfg = dict(WORKLOAD)
+    cfg = dict(CONFIGS[args.config])
     if args.small:
-        cfg.update(batch=2, img=224, depth=2)
+        cfg.update(batch=2, img=(224, 224), depth=7)
     from attentionshift_b200 import ops
     bb, head = build_models(cfg, dev)
     inputs = make_inputs(cfg, rank)
@@ -220,35 +261,20 @@ def run_ours(args):
         parallel.barrier()
         torch.cuda.synchronize()
 
-    # per-entry-point device timing: the library's timing slots are recorded on the launching stream around every C-ABI
-    # call -- inside the backbone's CUDA graph too (captured during the first warm-up step), so the kernel times below
-    # come from the timed region itself (its last step)
-    if not os.environ.get('AS_BENCH_NO_TIMERS'):
-        ops.TIMERS.enable()
     # the clock sampler starts BEFORE the warm-up: the first NVML queries of a process are slow and take a driver lock that
     # stalls kernel launches (seen as a 100+ ms hiccup in whichever loop ran first); its samples are reset when timing starts
     sampler = ClockSampler(local) if rank == 0 else None     # one per job: NVML calls serialise on a driver lock shared by all ranks
     if sampler is not None:
         sampler.start()
-    for _ in range(max(args.warmup, 1)):
-        ops.TIMERS.begin_step()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         one_step(bb, head, img_dev, inputs, False)
     torch.cuda.synchronize()
 
-    # ---- device-resident timing (value)
-    barrier()
+    # ---- device-resident timing (value): library timing slots OFF, nothing but the step's own work on the stream
     if sampler is not None:
         sampler.rows = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        ops.TIMERS.begin_step()
-        one_step(bb, head, img_dev, inputs, False)
-    e1.record()
-    barrier()
-    ms_dev = e0.elapsed_time(e1) / args.steps
-    fam = ops.TIMERS.summary() if ops.TIMERS.on else {}
-    ops.TIMERS.disable()
+    ms_dev = time_steps(lambda: one_step(bb, head, img_dev, inputs, False), args.steps, barrier)
 
     # ---- end-to-end timing (e2e): pinned host image -> device every step, masks back to the host every step.
     # The copy of step i+1 runs on a side stream while step i computes (double buffer); every copy is inside the timed region.
@@ -277,7 +303,7 @@ def run_ours(args):
 
     for f in freed:
         f.record()
-    e2e_loop(max(args.warmup, 1))          # untimed: first use of the pinned mask buffers / copy stream (cudaHostAlloc is slow)
+    e2e_loop(warm)                         # untimed: first use of the pinned mask buffers / copy stream (cudaHostAlloc is slow)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -288,20 +314,51 @@ def run_ours(args):
     if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-
     ms_dev, ms_e2e = parallel.max_over_ranks([ms_dev, ms_e2e], device=dev)     # the slowest rank defines the step
-    n_ours, n_all = count_launches(lambda: one_step(bb, head, img_dev, inputs, False)) if rank == 0 else (None, None)
+
+    # ---- per-entry-point device times: a SEPARATE, untimed pass with the library's timing slots on (they are event-record
+    # nodes inside a re-captured backbone graph and ~100 extra event records per step: kept out of the timed regions above)
+    fam = {}
+    n_ours = n_all = None
+    if rank == 0:
+        ops.TIMERS.enable()
+        if hasattr(bb, '_graphs'):
+            bb._graphs.clear()
+        for _ in range(3):
+            ops.TIMERS.begin_step()
+            one_step(bb, head, img_dev, inputs, False)
+        fam = ops.TIMERS.summary()
+        ops.TIMERS.disable()
+        if hasattr(bb, '_graphs'):
+            bb._graphs.clear()
+        n_ours, n_all = count_launches(lambda: one_step(bb, head, img_dev, inputs, False))
+
+    # ---- the reference's configuration untouched (all 12 full fp32 maps, FPN on, eager launches): cfg2, one GPU
+    ref_cfg = None
+    if rank == 0 and world == 1 and args.config == 'cfg2' and not args.no_reference_config and not args.small:
+        del bufs
+        bb._graphs.clear()
+        torch.cuda.empty_cache()
+        bb2, head2 = build_models(cfg, dev, reference_config=True)
+        for _ in range(2):
+            one_step(bb2, head2, img_dev, inputs, False)
+        ms2 = time_steps(lambda: one_step(bb2, head2, img_dev, inputs, False), max(2, min(args.steps, 4)), lambda: torch.cuda.synchronize())
+        ref_cfg = dict(value=round(cfg['batch'] / (ms2 * 1e-3), 2), unit='images/s', ms_per_step=round(ms2, 3),
+                       what='VisionTransformerDet exactly as configs/mae/attnshift_voc12aug.py builds it: all 12 head-mean maps as full fp32 '
+                            '[B,T,T] tensors (attn_layers=None, attn_format=full), with_fpn=True, eager launches (cuda_graph=False)')
+        del bb2, head2
 
     if rank == 0:
         pk = peaks()
-        B, T, C = cfg['batch'], 1 + (cfg['img'] // 16) ** 2 + cfg['n_point_tokens'], cfg['embed']
-        N = (cfg['img'] // 16) ** 2
+        H, W = cfg['img']
+        N = (H // 16) * (W // 16)
+        B, T, C = cfg['batch'], 1 + N + cfg['n_point_tokens'], cfg['embed']
         att = fam.get('as_mhsa_fwd', {})
         flops_attn = 4.0 * T * T * C * B                      # SDPA part of F_attn, per launch (one layer, whole batch)
         roof = None
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'ncu_mhsa_traffic.json')      # dram bytes / launch from the committed ncu capture
-        if os.path.exists(tpath) and not args.small:
+        if os.path.exists(tpath) and not args.small and args.config == 'cfg2':
             try:
                 traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
             except Exception:
@@ -311,110 +368,125 @@ def run_ours(args):
             roof = dict(kernel='mhsa_fwd2_kernel (tcgen05 flash attention, one launch = one layer x batch)', bound='tensor',
                         achieved=round(ach, 1), peak=pk['tf_sus'], unit='TFLOP/s', frac=round(ach / pk['tf_sus'], 4),
                         traffic=traffic, peak_source=pk['src'] + ' sustained bf16 GEMM', share_of_step=round(att['ms'] / ms_dev, 3))
-        ms_name = next((k for k in ('as_mean_shift_fused', 'as_mean_shift_tc', 'as_mean_shift') if fam.get(k, {}).get('n')), 'as_mean_shift')
+        ms_name = next((k for k in ('as_mean_shift_v2', 'as_mean_shift_fused', 'as_mean_shift_tc', 'as_mean_shift') if fam.get(k, {}).get('n')),
+                       'as_mean_shift')
         msf = fam.get(ms_name, {})
         K = cfg['n_obj'] * cfg['seeds']
         b_alg = ((cfg['iters'] + 1) * N * C * 4 + K * N * 4 + 2 * K * C * 4) * B      # SURVEY 8d B_alg per image x images
         roof2 = None
         if msf.get('n'):
             ach2 = b_alg / (msf['ms'] / msf['n'] * 1e-3) / 1e9
-            what = {'as_mean_shift_fused': 'one persistent cooperative kernel + the token split kernel',
+            what = {'as_mean_shift_v2': 'one persistent cooperative kernel, two CTAs per SM, + the token split kernel',
+                    'as_mean_shift_fused': 'round-1 persistent kernel + the token split kernel',
                     'as_mean_shift_tc': '~50 launches', 'as_mean_shift': 'fp32 CUDA-core kernels'}[ms_name]
             traffic2 = None
-            t2path = os.path.join(ROOT, 'profiles', 'ncu_msfused_traffic.json')      # dram bytes / launch from the committed ncu capture
-            if ms_name == 'as_mean_shift_fused' and os.path.exists(t2path) and not args.small:
+            t2path = os.path.join(ROOT, 'profiles', 'ncu_msv2_traffic.json')      # dram bytes / launch from the committed ncu capture
+            if ms_name == 'as_mean_shift_v2' and os.path.exists(t2path) and not args.small and args.config == 'cfg2':
                 try:
                     traffic2 = json.load(open(t2path)).get('dram_bytes_per_launch')
                 except Exception:
                     traffic2 = None
-            roof2 = dict(kernel='%s (whole on-device attention-shift loop, all images of the batch; %s)' % (ms_name, what), bound='hbm', achieved=round(ach2, 1),
-                         peak=pk['hbm'], unit='GB/s', frac=round(ach2 / pk['hbm'], 4), traffic=traffic2, peak_source=pk['src'])
-        line = dict(metric='images/sec at 1024^2 bs8 ViT-B attn-shift', value=round(world * B / (ms_dev * 1e-3), 2), unit='images/s',
-                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=round(ms_dev, 3), higher_is_better=True,
+            roof2 = dict(kernel='%s (whole on-device attention-shift loop, all images of the batch; %s)' % (ms_name, what), bound='hbm',
+                         achieved=round(ach2, 1), peak=pk['hbm'], unit='GB/s', frac=round(ach2 / pk['hbm'], 4), traffic=traffic2,
+                         peak_source=pk['src'], ms_per_call=round(msf['ms'] / msf['n'], 4), algorithmic_bytes=int(b_alg))
+        line = dict(metric='images/sec at 1024^2 bs8 ViT-B attn-shift' if args.config == 'cfg2' else 'images/sec, ' + cfg['name'],
+                    value=round(world * B / (ms_dev * 1e-3), 2), unit='images/s',
+                    n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=round(ms_dev, 3), higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f16 operands / f32 accumulate (ViT GEMMs + attention), f32 (attention shift)',
-                    data='synthetic (random-init ViT-B/16 weights, randn images, random GT points)',
-                    config=dict(workload=cfg['name'], per_gpu_batch=B, fpn=False, l2='inputs larger than L2 (per-step working set >> 126 MB)',
-                                backbone='one CUDA graph per forward (cuda_graph=True)', kernel_times='library timing slots, last step of the timed region',
-                                attn_maps='last 7 layers (the ones seed_pseudo_gt reads)', small=bool(args.small)),
+                    data='synthetic (random-init ViT weights, randn images, random GT points)',
+                    config=dict(workload=cfg['name'], per_gpu_batch=B, mode='forward-only, no collective (every rank runs its own batch)',
+                                fpn=False, l2='inputs larger than L2 (per-step working set >> 126 MB)',
+                                backbone='one CUDA graph per forward (cuda_graph=True); head-mean maps of the 7 layers seed_pseudo_gt reads, '
+                                         'produced as roll-out operands (attn_layers=7, attn_format=rollout)',
+                                kernel_times='library timing slots, separate untimed pass after the timed regions', small=bool(args.small)),
                     e2e=dict(value=round(world * B / (ms_e2e * 1e-3), 2), unit='images/s', ms_per_step=round(ms_e2e, 3),
                              h2d_bytes_per_step=int(img_host.nbytes), d2h_bytes_per_step=int(d2h)),
                     gpu_launches=n_ours, all_launches=n_all, clocks=sampler.summary(), roofline=roof, roofline_attnshift=roof2,
+                    reference_config=ref_cfg,
                     kernel_ms_per_step={k: round(v['ms'], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])})
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(cfg, steps=1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        parallel.barrier()
         torch.distributed.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_one_image(cfg, seed):
-    """The reference algorithm (CPU oracle port, same torch ops as the reference) on ONE image of the workload."""
-    import torch.nn.functional as F
-    from attentionshift_b200.synthetic import structured_scene, vit_state_dict
+def cpu_one_image(cfg, which=0):
+    """The reference algorithm (CPU oracle port, same torch ops as the reference) on ONE image of the workload -- image ``which`` of
+    the very batch the CUDA arm runs (same generator), the same dataflow (backbone outputs -> roll-out -> CAM boxes -> attention
+    shift), the same selections and the same seed count."""
+    from attentionshift_b200.synthetic import vit_state_dict
     from oracle import attnshift as O
     from oracle import vit as V
-    S = cfg['img']
-    hp = S // 16
-    g = torch.Generator().manual_seed(seed)
-    sd = cpu_one_image.sd if hasattr(cpu_one_image, 'sd') else vit_state_dict(cfg['embed'], cfg['depth'], cfg['heads'], S,
-                                                                            n_point_tokens=cfg['n_point_tokens'], seed=0)
-    cpu_one_image.sd = sd
-    img = torch.randn(1, 3, S, S, generator=g)
+    H, W = cfg['img']
+    hp, wp = H // 16, W // 16
+    n_pt = cfg['n_point_tokens']
+    if not hasattr(cpu_one_image, 'cache') or cpu_one_image.cache[0] != cfg['name']:
+        sd = vit_state_dict(cfg['embed'], cfg['depth'], cfg['heads'], H if H == W else 224, n_point_tokens=n_pt, seed=0)
+        cpu_one_image.cache = (cfg['name'], sd, make_inputs(cfg, 0, pin=False))
+    _, sd, (img, gt_points, pos_inds, gt_index, labels) = cpu_one_image.cache
+    i = which % cfg['batch']
+    n = cfg['n_obj']
     t0 = time.time()
     with torch.no_grad():
-        out = V.backbone_forward(img, sd, cfg['depth'], cfg['heads'], n_point_tokens=cfg['n_point_tokens'])
+        out = V.backbone_forward(img[i:i + 1], sd, cfg['depth'], cfg['heads'], n_point_tokens=n_pt)
         t1 = time.time()
-        rows = O.rollout_rows(out['attns'][-cfg['cam_layer']:], cfg['n_point_tokens'])
-        # attention-shift stage on the structured scene (SURVEY 8d): random-init features carry no instance structure
-        sc = structured_scene(hp, hp, cfg['embed'], cfg['n_obj'], seed=seed, noise=0.5)
-        up = F.interpolate(sc['cams_low'].reshape(-1, 1, hp, hp), (S, S), mode='bilinear').reshape(7, cfg['n_obj'], S, S)
-        for l in range(7):
-            for j in range(cfg['n_obj']):
-                O.bbox_from_cam(up[l, j].clone(), sc['gt_points'][j], 0.2, 0.5, (S, S))
-        O.attention_shift_image(up, sc['gt_index'], sc['rois'], sc['vit_feat'].clone(), sc['gt_points'], sc['gt_labels'],
-                                mean_shift_times=cfg['iters'], n_points=20)
+        rows = O.rollout_rows(out['attns'][-cfg['cam_layer']:], n_pt)[0]      # slab shortcut (100 rows), NOT the reference's full T x T chain (RH:1265)
+        low, up = O.cams_from_rollout(rows, pos_inds[i], n_pt, hp, wp)
+        boxes = torch.stack([torch.cat([O.bbox_from_cam(up[l, j].clone(), gt_points[i][j], 0.2, 0.5, (H, W))[0] for j in range(n)])
+                             for l in range(cfg['cam_layer'])])
+        pb = boxes[gt_index[i], torch.arange(n)]
+        O.attention_shift_image(up, gt_index[i], pb, out['last_feat'][0, 1:].t().unflatten(-1, (hp, wp)).contiguous(), gt_points[i],
+                                labels[i], pos_mask_thr=0.6, neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, obj_tau=0.85,
+                                mean_shift_times=cfg['iters'], n_points=cfg['seeds'])
     t2 = time.time()
     return t2 - t0, t1 - t0, t2 - t1
 
 
+CPU_SAMPLE = ('one image of the workload batch per step (the same image, selections and {seeds} seeds / {iters} iterations as the CUDA arm): '
+              'oracle port of the reference on torch CPU fp32, all usable host threads; roll-out as the 100-row slab (not the '
+              "reference's full T x T chain, RH:1265, which would add ~0.8 s / image)")
+
+
 def cpu_baseline(cfg, steps=1):
     torch.set_num_threads(usable_cpus())
-    ts = [cpu_one_image(cfg, 100 + i) for i in range(steps)]
+    ts = [cpu_one_image(cfg, i) for i in range(steps)]
     tot = sum(t[0] for t in ts) / len(ts)
     return dict(value=round(1.0 / tot, 4), unit='images/s', cores=usable_cpus(), kind='port',
-                sample=f'{steps} image(s) of the workload (1/{cfg["batch"]} batch): ViT forward {ts[0][1]:.1f}s + roll-out/attention-shift {ts[0][2]:.1f}s; '
-                       'torch CPU fp32, all host threads; attention-shift stage on the structured synthetic scene (20 seeds as hard-coded in the reference)')
+                sample=CPU_SAMPLE.format(**cfg) + f'; ViT forward {ts[0][1]:.1f}s + roll-out / attention shift {ts[0][2]:.1f}s')
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    cfg = dict(WORKLOAD)
+    cfg = dict(CONFIGS[args.config])
     if args.small:
-        cfg.update(batch=2, img=224, depth=2)
+        cfg.update(batch=2, img=(224, 224), depth=7)
     torch.set_num_threads(usable_cpus())
     budget = 240.0
     t_all = time.time()
     done_w = 0
     for _ in range(min(args.warmup, 1)):
-        cpu_one_image(cfg, 7)
+        cpu_one_image(cfg, 0)
         done_w += 1
     per = []
     for i in range(args.steps):
         if per and (time.time() - t_all) + per[-1] > budget:
             break
-        per.append(cpu_one_image(cfg, 100 + i)[0])
+        per.append(cpu_one_image(cfg, i)[0])
     ms = 1e3 * sum(per) / len(per)
     v = round(1e3 / ms, 4)
-    line = dict(impl='reference', metric='images/sec at 1024^2 bs8 ViT-B attn-shift', value=v, unit='images/s', n_gpus=args.gpus,
+    line = dict(impl='reference', metric='images/sec at 1024^2 bs8 ViT-B attn-shift' if args.config == 'cfg2' else 'images/sec, ' + cfg['name'],
+                value=v, unit='images/s', n_gpus=args.gpus,
                 steps=len(per), warmup=done_w, ms_per_step=round(ms, 1), higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32', data='synthetic (same generator as the CUDA arm)',
-                config=dict(workload=cfg['name'], per_gpu_batch=cfg['batch'], small=bool(args.small),
+                dtype='f32', data='synthetic (the CUDA arm\'s own batch: same generator, same selections)',
+                config=dict(workload=cfg['name'], per_gpu_batch=cfg['batch'], small=bool(args.small), mode='forward-only, no collective',
                             note='each step = ONE image of the batch (bounded sample); the reference algorithm is per-image, images/s is per host'),
                 cpu_baseline=dict(value=v, unit='images/s', cores=usable_cpus(), kind='port',
-                                  sample='one image per step; oracle port of the reference (the python reference cannot travel to the GPU box)'),
+                                  sample=CPU_SAMPLE.format(**cfg) + ' (the python reference cannot travel to the GPU box)'),
                 e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 

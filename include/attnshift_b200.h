@@ -60,6 +60,14 @@ int as_mhsa_set_variant(int variant);
 int as_attn_headmean(const void* q, const void* k, const float* m, const float* l, float* out, int ld, float* rowsum_part,
                      int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads,
                      as_stream_t stream);
+/* Same, producing only what the roll-out (RH:1257-1272 restricted to the rows RH:2272 reads) consumes of a layer
+ * (persistent schedule, rowsum_slices = 4): out may be NULL -- transposed pair + row sums only, for every layer but the last;
+ * q_row0 > 0 (needs t_hi = NULL) -- only the query tiles containing rows [q_row0, T) are computed, for the last layer, whose map
+ * enters the roll-out through its point-token rows alone.  Rows of out / rowsum_part before the first computed tile are not
+ * written. */
+int as_attn_headmean_ex(const void* q, const void* k, const float* m, const float* l, float* out, int ld, float* rowsum_part,
+                        int rowsum_slices, void* t_hi, void* t_lo, int ldt, float t_scale, int B, int T, int heads, int q_row0,
+                        as_stream_t stream);
 
 /* Batched f16 x f16 -> f32 GEMM on tcgen05: out[b] = resid[b] + alpha * x[b] w[b]^T (resid may alias out / be NULL). */
 int as_bgemm_f16_f32(const void* x_f16, const void* w_f16, float* out, const float* resid, int batch, int M, int N, int K,
@@ -176,6 +184,20 @@ int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img
                         const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois,
                         int n_tot, int S, float* proto, float* sim_out, int n_shift, double tau0, double temp,
                         int clamp0, int* trace, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* Second-generation persistent kernel (round 2): 128 tokens per CTA so that two CTAs of different images share an SM (one
+ * streams while the other sits in the latency-bound part of its iteration), similarities resident in TMEM, update
+ * accumulators per 128-channel block.  Lifts the round-1 limits: up to 256 seed columns per image (kmax = max n_obj * S),
+ * up to 16 instances per image (8 when kmax <= 64), any C % 128 == 0 up to 1024 (ViT-L).  max_obj = max_i img_nobj[i].
+ * as_mean_shift_v2_supported() tells whether the kernel takes a problem; as_mean_shift_v2 returns AS_ERR_BAD_ARG when it
+ * does not, or when one image's CTAs cannot be co-resident.  Replaces RH:830-854 + RH:882-908. */
+int as_mean_shift_v2_supported(int N, int C, int kmax, int max_obj);
+size_t as_mean_shift_v2_workspace(int n_img, int N, int C, int kmax, int max_obj);
+void as_mean_shift_v2_debug(unsigned long long* buf);
+int as_mean_shift_v2(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
+                     const int* img_first, const int* img_nobj, int kmax, int max_obj, const float* rois, int n_tot, int S,
+                     float* proto, float* sim_out, int n_shift, double tau0, double temp, int clamp0, int* trace,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
 

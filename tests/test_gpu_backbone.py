@@ -86,3 +86,30 @@ def test_cuda_graph_replay_equals_eager():
             m.blocks[0].mlp.fc1.bias.add_(0.5)
     a, b = eager(x), graph(x)
     assert torch.equal(a['last_feat'], b['last_feat'])
+
+
+@pytest.mark.parametrize('img,n_pt', [(224, 100), (320, 12)])
+def test_rollout_format_equals_full_maps(img, n_pt):
+    """attn_format='rollout' (transposed operand + row sums for every layer but the last, point-token rows of the last one) must
+    give the roll-out slab the SAME bits as the reference-shaped production of full fp32 maps, and the partially written last
+    map must hold exactly the full map's rows from its first computed tile on."""
+    from attentionshift_b200 import attention_shift as AS
+    from attentionshift_b200.registry import build_backbone
+    embed, heads, depth = 128, 2, 8
+    sd = vit_state_dict(embed, depth, heads, img, n_point_tokens=n_pt, seed=6)
+    outs = {}
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, img, img, generator=gen).cuda()
+    for fmt in ('full', 'rollout'):
+        m = build_backbone(dict(type='VisionTransformerDet', img_size=img, patch_size=16, embed_dim=embed, depth=depth, num_heads=heads,
+                                mlp_ratio=4, qkv_bias=True, with_fpn=False, last_feat=True, return_attention=True,
+                                point_tokens_num=n_pt, with_point_head=False, attn_layers=7, attn_format=fmt, out_indices=[depth - 1]))
+        m.load_state_dict(sd, strict=False)
+        outs[fmt] = m.cuda().eval()(x)
+    full, lean = outs['full']['attns'][-7:], outs['rollout']['attns'][-7:]
+    assert all(a.numel() == 0 for a in lean[:-1]) and lean[-1].shape == full[-1].shape
+    r_full, r_lean = AS.rollout_rows(full, n_pt), AS.rollout_rows(lean, n_pt)
+    assert torch.equal(r_full, r_lean)
+    v0 = lean[-1]._as_valid_from
+    assert v0 <= full[-1].shape[1] - n_pt and torch.equal(lean[-1][:, v0:], full[-1][:, v0:])
+    assert torch.equal(outs['full']['last_feat'], outs['rollout']['last_feat'])
