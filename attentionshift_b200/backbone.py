@@ -19,6 +19,55 @@ from . import ops
 from .registry import BACKBONES
 
 
+class LazyOutputs(dict):
+    """The forward's return dict with entries that are computed on first access.  ``org_feats`` / ``feature`` (VTD:246-256, 259-262)
+    are transposed COPIES of the residual stream at four layers (+ the FPN on top): ~1 GB of traffic at bs8 1024^2 that
+    ``seed_pseudo_gt`` never reads.  Values are identical to the eager ones; whoever reads a key pays for it, once."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._thunks = {}
+        self._arm = None
+
+    def fresh(self):
+        """A new dict over the same eager entries with the lazy ones re-armed (the CUDA-graph path hands the same output buffers
+        out after every replay: what was materialised from the previous replay's contents must not be served again)."""
+        new = LazyOutputs({k: v for k, v in super().items() if k not in self._lazy_keys()})
+        if self._arm is not None:
+            self._arm(new)
+        return new
+
+    def _lazy_keys(self):
+        return getattr(self, '_lazy', set())
+
+    def set_lazy(self, key, fn):
+        self._thunks[key] = fn
+        self._lazy = self._lazy_keys() | {key}
+        super().__setitem__(key, None)
+
+    def _force(self, key):
+        fn = self._thunks.pop(key, None)
+        if fn is not None:
+            super().__setitem__(key, fn())
+
+    def __getitem__(self, key):
+        self._force(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        for k in list(self._thunks):
+            self._force(k)
+        return super().items()
+
+    def values(self):
+        for k in list(self._thunks):
+            self._force(k)
+        return super().values()
+
+
 def trunc_normal_(t, std=.02):
     return nn.init.trunc_normal_(t, std=std, a=-2., b=2.)
 
@@ -290,7 +339,7 @@ class VisionTransformerDet(nn.Module):
             self._graphs[key] = ent
         ent['static_in'].copy_(x, non_blocking=True)
         ent['graph'].replay()
-        return ent['out']
+        return ent['out'].fresh()
 
     @torch.no_grad()
     def _forward_eager(self, x):
@@ -311,25 +360,41 @@ class VisionTransformerDet(nn.Module):
             if self.return_attention:
                 attns.append(a)
             if i in self.out_indices:
-                xp = xs.view(B, T, C)[:, 1:, :][:, :-Tp].permute(0, 2, 1).reshape(B, -1, Hp, Wp)
-                features.append(xp.contiguous())
+                features.append(xs)                             # the block's output buffer; transposed on demand (LazyOutputs)
             if self.last_feat and (not self.recompute_last_feat) and i == depth - 1:
                 last_feat = xs.view(B, T, C)[:, :-Tp]
         xo = xs.view(B, T, C)
-        org_features = torch.stack(features, dim=1)
-        if self.with_fpn:
-            fops = [self.fpn1, self.fpn2, self.fpn3, self.fpn4]
-            for i in range(len(features)):
-                features[i] = fops[i](features[i])
         point_tokens = xo[:, -Tp:]
-        ret = dict(org_feats=org_features, feature=tuple(features), point_tokens=point_tokens)
+        ret = LazyOutputs(point_tokens=point_tokens)
+
+        def arm(d):
+            memo = {}
+
+            def raw_features():                                 # VTD:246-248: [B,C,Hp,Wp] copies of the patch tokens at out_indices
+                if 'f' not in memo:
+                    memo['f'] = [x_.view(B, T, C)[:, 1:, :][:, :-Tp].permute(0, 2, 1).reshape(B, -1, Hp, Wp).contiguous() for x_ in features]
+                return memo['f']
+
+            def fpn_features():                                 # VTD:253-256
+                f = list(raw_features())
+                if self.with_fpn:
+                    fops = [self.fpn1, self.fpn2, self.fpn3, self.fpn4]
+                    for j in range(len(f)):
+                        f[j] = fops[j](f[j])
+                return tuple(f)
+
+            d.set_lazy('org_feats', lambda: torch.stack(raw_features(), dim=1))
+            d.set_lazy('feature', fpn_features)
+            d._arm = arm
+
+        arm(ret)
         if self.with_point_head:
-            ret.update(dict(outputs_class=self.class_embed(point_tokens),
-                            outputs_coord=self.bbox_embed(point_tokens).sigmoid()))
+            ret['outputs_class'] = self.class_embed(point_tokens)
+            ret['outputs_coord'] = self.bbox_embed(point_tokens).sigmoid()
         if self.return_attention and self.last_feat:
-            ret.update(dict(attns=attns))
+            ret['attns'] = attns
         if self.last_feat:
-            ret.update(dict(last_feat=last_feat))
+            ret['last_feat'] = last_feat
         return ret
 
 

@@ -449,6 +449,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
 #pragma unroll 8
           for (int t = g4; t < TOK; t += 4) {
             const float e = expf((sims_s[t * SIM_LD + col] - cmax) * inv_tt);
+            sims_s[t * SIM_LD + col] = e;                       // the assignment only needs weight = e / Z: no second exp
             z += tok(t) < p.N ? e : 0.f;
           }
         }
@@ -525,7 +526,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int col = j * p.S + min(s + i, p.S - 1);
-                w4[i] = expf((row[col] - st_s[col * 4 + 1]) * st_s[col * 4]) * st_s[col * 4 + 2];
+                w4[i] = row[col] * st_s[col * 4 + 2];            // e (written by the statistics phase) / Z
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -580,9 +581,10 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
             tc_wait_ld();
             float* dst = p.proto_part + ((size_t)img * p.G + q) * LDK * p.C + cb * 128 + quad * 32 + lane;
 #pragma unroll
-            for (int col = 0; col < LDK; ++col)
-              if (col < kb_cols)
-                dst[(size_t)col * p.C] = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]) * sc_s[col * 2 + 1];
+            for (int col = 0; col < LDK; ++col) {                 // running pointer: one 64-bit add per row, no wide multiply
+              if (col < kb_cols) *dst = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]) * sc_s[col * 2 + 1];
+              dst += p.C;
+            }
           }
           tc_fence_before();
         }
@@ -632,16 +634,27 @@ __global__ void fused_split_tokens(const float* __restrict__ feats, long long fs
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
   const float* f = feats + img * fstride + (long long)n * C;
+  const int lane = lane_id();
   float ss = 0.f;
-  for (int c = lane_id(); c < C; c += 32) ss += f[c] * f[c];
+  for (int c = lane * 4; c < C; c += 128) {                    // C % 128 == 0: float4 loads, 8-byte stores
+    const float4 t = *reinterpret_cast<const float4*>(f + c);
+    ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
   const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
-  if (lane_id() == 0) den[(size_t)img * N + n] = nrm;
+  if (lane == 0) den[(size_t)img * N + n] = nrm;
   const size_t o = ((size_t)img * N + n) * C;
-  for (int c = lane_id(); c < C; c += 32) {
-    const float v = f[c] / nrm * OP_SCALE;
-    const __half h = __float2half_rn(v);
-    hi[o + c] = h;
-    lo[o + c] = __float2half_rn(v - __half2float(h));
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 t = *reinterpret_cast<const float4*>(f + c);
+    const float x[4] = {t.x, t.y, t.z, t.w};
+    __half h4[4], l4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = x[e] / nrm * OP_SCALE;
+      h4[e] = __float2half_rn(v);
+      l4[e] = __float2half_rn(v - __half2float(h4[e]));
+    }
+    *reinterpret_cast<uint2*>(hi + o + c) = *reinterpret_cast<uint2*>(h4);
+    *reinterpret_cast<uint2*>(lo + o + c) = *reinterpret_cast<uint2*>(l4);
   }
 }
 }  // namespace

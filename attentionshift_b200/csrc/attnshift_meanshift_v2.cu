@@ -31,6 +31,8 @@
 // and one more (unmasked) affinity pass for the returned similarity maps.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
+#include <algorithm>
 
 using namespace asb;
 
@@ -47,7 +49,7 @@ template <int KP> struct Cfg {
   static constexpr int NBUF = KP == 256 ? 1 : 2;             // update accumulator buffers in TMEM
   static constexpr int TM_COLS = KP == 64 ? 256 : 512;
   static constexpr int MAXOBJ = KP == 64 ? 8 : 16;
-  static constexpr int MISC = MAXOBJ * TOKC * 5 + TOKC * 4 + 4 * KP * 3 * 4 + KP * 6 * 4 + 512;
+  static constexpr int MISC = MAXOBJ * TOKC * 5 + TOKC * 4 + 4 * KP * 3 * 4 + KP * 6 * 4 + 2 * KP + 512;
   static constexpr int SMEM = 1024 + NA * STAGE + 2 * BTILE + MISC;
 };
 
@@ -80,7 +82,9 @@ struct V2Params {
   float* z_part;               // [n_img][G][KP]
   float* proto_part;           // [n_img][G][KP][C]
   unsigned* bar;               // [n_img] monotonic group-barrier counters
+  unsigned* sched;             // [2 + #SMs] work tickets of the two halves of the image groups, CTAs seen per SM
   unsigned long long* dbg;     // optional [grid][16] accumulated ns per phase
+  unsigned stagger_ns;         // start delay of the second half of the image groups (see the kernel)
 };
 
 __device__ __forceinline__ void group_barrier2(unsigned* ctr, unsigned target) {
@@ -139,7 +143,9 @@ __device__ __forceinline__ float warp_col_reduce(float (&a)[32], int lane) {
 }
 
 template <int KP>
-__global__ void __launch_bounds__(V2_THREADS, KP == 64 ? 2 : 1)
+// KP = 64: two CTAs per SM.  Registers are granted per 4-warp granule, so the 6 warps of a CTA count as 8: the cap must be
+// 65536 / (2 x 256) = 128 per thread (launch bounds of 256 threads), not the 168 that 192 threads would suggest.
+__global__ void __launch_bounds__(KP == 64 ? 256 : V2_THREADS, KP == 64 ? 2 : 1)
 mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_constant__ CUtensorMap tm_lo64,
                      const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_plo,
                      const V2Params p) {
@@ -157,7 +163,9 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
   float* st_s = red_s + 4 * 3 * KP;                            // [KP][4] 1/tt, column max, 1/Z, tau
   float* sc_s = st_s + KP * 4;                                 // [KP][2] weight scale 2^k of the seed, 2^-k / OP_SCALE
   int8_t* idx_s = reinterpret_cast<int8_t*>(sc_s + KP * 2);    // [MAXOBJ][TOKC] assigned seed of the previous iteration
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(idx_s + MAXOBJ * TOKC) + 7) & ~(uintptr_t)7);
+  uint8_t* cj_s = reinterpret_cast<uint8_t*>(idx_s + MAXOBJ * TOKC);       // [KP] instance of a seed column (255: unused column)
+  uint8_t* cs_s = cj_s + KP;                                   // [KP] seed index of the column inside its instance
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(cs_s + KP) + 7) & ~(uintptr_t)7);
   uint64_t* a_full = bars;             // NA (<= 3)
   uint64_t* a_empty = bars + 3;        // NA
   uint64_t* b_full = bars + 6;         // 2
@@ -172,8 +180,26 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
   const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
   const bool worker = warp >= 2;
   const int tl = quad * 32 + lane;                             // worker: local token = TMEM lane = row of the MMA tile
+  // Which (image group, rank) a CTA works on is decided at run time from WHERE it landed: the first CTA to arrive on an SM takes
+  // a ticket of the first half of the image groups, the second one a ticket of the second half (falling back to the other half
+  // when its own is exhausted), and the second half starts `stagger_ns` late.  So on every SM one CTA streams tokens (TMA /
+  // tensor pipe) while the other is in the latency-bound part of its iteration (statistics, assignment, group barriers);
+  // without the offset all images march in lock step and the co-resident CTAs only get in each other's way.
   const int groups = gridDim.x / p.G;
-  const int grp = blockIdx.x / p.G, q = blockIdx.x % p.G;
+  const int groups_a = (groups + 1) / 2;
+  __shared__ int s_ticket[2];
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned slot = atomicAdd(p.sched + 2 + smid, 1u);
+    int half = (int)(slot & 1u);
+    const int need[2] = {groups_a * p.G, (groups - groups_a) * p.G};
+    int t = (int)atomicAdd(p.sched + half, 1u);
+    if (t >= need[half]) { half ^= 1; t = (int)atomicAdd(p.sched + half, 1u); }
+    s_ticket[0] = half; s_ticket[1] = t;
+  }
+  __syncthreads();
+  const int grp = (s_ticket[0] ? groups_a : 0) + s_ticket[1] / p.G, q = s_ticket[1] % p.G;
   const int kblocks = p.C / 64;
   const int cblocks = p.C / 128;
 
@@ -201,6 +227,13 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
   uint32_t ucount = 0;                          // MMA + workers: channel blocks of the update so far
   uint32_t wcount = 0;                          // MMA: update phases so far
 
+  if (p.stagger_ns && groups >= 2 && grp >= groups_a) {
+    if (threadIdx.x == 0) {
+      const uint64_t t0 = global_timer_ns();
+      while (global_timer_ns() - t0 < p.stagger_ns) __nanosleep(256);
+    }
+    __syncthreads();
+  }
   uint64_t t_prev = global_timer_ns();
   auto mark = [&](int k) {
     if (p.dbg && threadIdx.x == 64) { const uint64_t t = global_timer_ns(); p.dbg[blockIdx.x * 16 + k] += t - t_prev; t_prev = t; }
@@ -220,6 +253,11 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
       const float dn = valid ? p.den[(size_t)img * p.N + n_tok] : 1.f;
       den_s[tl] = dn;
       for (int j = 0; j < MAXOBJ; ++j) { idx_s[j * TOKC + tl] = -1; w_s[j * TOKC + tl] = 0.f; }
+      for (int col = tl; col < KP; col += TOKC) {
+        const int cj = col < kb_cols ? col / p.S : 255;
+        cj_s[col] = (uint8_t)cj;
+        cs_s[col] = (uint8_t)(col < kb_cols ? col - cj * p.S : 0);
+      }
       if (valid)
         for (int j = 0; j < nobj; ++j)
           if (in_box2(patch_box2(p.rois + 4 * (o0 + j), p.hp, p.wp), n_tok, p.wp)) boxmask |= 1u << j;
@@ -364,22 +402,53 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
         tc_fence_after();
         mark(10);
         const float alpha = 1.f / (OP_SCALE * OP_SCALE);
-        int j = 0, s = 0;                                       // instance / seed of the running column
+        float* hv_s = w_s;                                      // value at the previously assigned seed, per (instance, token): w_s is dead here
+        int hits = 0;                                           // hit columns seen so far = instance index of the next one
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
           if (ch * 32 >= kb_cols) break;
           uint32_t raw[32];
           tmem_ld_32x32(tm_row + ch * 32, raw);
+          // per-chunk bit masks instead of per-column bookkeeping (no branches, no counters in the 32-column loop):
+          //   vmask: columns that exist; onmask: columns whose instance's box holds this token (every column on the last pass);
+          //   hitmask: the column of each instance this token was assigned to in the previous iteration
+          const int nc = kb_cols - ch * 32;
+          const unsigned vmask = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
+          unsigned onmask = 0, hitmask = 0;
+          if (valid) {
+            if (last) onmask = vmask;
+            for (int jj = 0; jj < nobj; ++jj) {
+              const int c0 = jj * p.S - ch * 32, c1 = c0 + p.S;                  // the instance's columns, chunk-relative
+              if (!last && ((boxmask >> jj) & 1u) && c1 > 0 && c0 < 32) {
+                const unsigned lo = c0 <= 0 ? 0xffffffffu : (0xffffffffu << c0);
+                const unsigned hi = c1 >= 32 ? 0xffffffffu : ((1u << c1) - 1u);
+                onmask |= lo & hi;
+              }
+              if (!last && it > 0) {
+                const int c = c0 + (int)idx_s[jj * TOKC + tl];
+                if ((unsigned)c < 32u) hitmask |= 1u << c;
+              }
+            }
+            onmask &= vmask;
+          }
+          const unsigned tvmask = valid ? vmask : 0u;
           tc_wait_ld();
-          unsigned hitmask = 0;                                   // bit c: the token was assigned to column c's seed last iteration
+          unsigned mymax = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const int col = ch * 32 + c;
-            const bool on = col < kb_cols && (last ? valid : ((boxmask >> j) & 1u) != 0);
-            raw[c] = __float_as_uint(on ? __uint_as_float(raw[c]) * alpha : 0.f);
-            if (valid && col < kb_cols && it > 0 && idx_s[j * TOKC + tl] == s) hitmask |= 1u << c;
-            if (++s == p.S) { s = 0; ++j; if (j >= MAXOBJ) j = MAXOBJ - 1; }
+            const float v = ((onmask >> c) & 1u) ? __uint_as_float(raw[c]) * alpha : 0.f;
+            raw[c] = __float_as_uint(v);
+            if (!last) {
+              // column maximum over the warp's 32 tokens: one REDUX on an order-preserving integer image of the float
+              const unsigned b = __float_as_uint(v);
+              const unsigned u = ((tvmask >> c) & 1u) ? (b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u)) : 0u;
+              const unsigned m = __reduce_max_sync(0xffffffffu, u);
+              if (lane == c) mymax = m;
+              // a valid token has exactly one hit column per instance, in instance order: the k-th hit belongs to instance k
+              if ((hitmask >> c) & 1u) hv_s[(hits + __popc(hitmask & ((1u << c) - 1u))) * TOKC + tl] = v;
+            }
           }
+          hits += __popc(hitmask);
           if (last) {
             // returned maps [o][s][n]: one coalesced row of this CTA's tokens per seed
             if (valid) {
@@ -395,30 +464,29 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
             }
           } else {
             tmem_st_32x32(tm_row + ch * 32, raw);
-            float a[32];                                          // one statistic at a time: keeps the live registers at ~2 x 32
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = (valid && ch * 32 + c < kb_cols) ? __uint_as_float(raw[c]) : -FLT_MAX;
-            const float rmx = warp_col_reduce<true>(a, lane);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = ((hitmask >> c) & 1u) ? __uint_as_float(raw[c]) : 0.f;
-            const float rsv = warp_col_reduce<false>(a, lane);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = ((hitmask >> c) & 1u) ? 1.f : 0.f;
-            const float rcv = warp_col_reduce<false>(a, lane);
-            red_s[(quad * 3 + 0) * KP + ch * 32 + lane] = rmx;
-            red_s[(quad * 3 + 1) * KP + ch * 32 + lane] = rsv;
-            red_s[(quad * 3 + 2) * KP + ch * 32 + lane] = rcv;
+            red_s[quad * KP + ch * 32 + lane] = __uint_as_float(mymax);     // still the integer image; decoded below
           }
         }
         if (!last) {
           tc_wait_st();
           tc_fence_before();
           workers_sync2();
+          // per column: max over the 4 warps, and the density partials = ordered sum / count over this CTA's tokens of the
+          // similarity at the seed the token was assigned to in the previous iteration (fixed token order: deterministic)
           for (int col = tl; col < kb_cols; col += TOKC) {
-            float mx = red_s[col], sv = red_s[KP + col], cv = red_s[2 * KP + col];
+            unsigned um = __float_as_uint(red_s[col]);
 #pragma unroll
-            for (int w = 1; w < 4; ++w) {
-              mx = fmaxf(mx, red_s[(w * 3 + 0) * KP + col]); sv += red_s[(w * 3 + 1) * KP + col]; cv += red_s[(w * 3 + 2) * KP + col];
+            for (int w = 1; w < 4; ++w) um = max(um, __float_as_uint(red_s[w * KP + col]));
+            const float mx = um == 0u ? -FLT_MAX : __uint_as_float(um ^ ((um >> 31) ? 0x80000000u : 0xffffffffu));
+            float sv = 0.f, cv = 0.f;
+            if (it > 0) {
+              const int jc = col / p.S, sc = col - jc * p.S;
+#pragma unroll 8
+              for (int t = 0; t < TOKC; ++t) {
+                const bool hit = idx_s[jc * TOKC + t] == sc;
+                sv += hit ? hv_s[jc * TOKC + t] : 0.f;
+                cv += hit ? 1.f : 0.f;
+              }
             }
             const size_t pi = ((size_t)img * p.G + q) * KP + col;
             p.colmax_part[pi] = mx; p.dens_part[pi * 2] = sv; p.dens_part[pi * 2 + 1] = cv;
@@ -467,9 +535,14 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
             // logit - max logit as (v - max) / tt: exactly 0 at the maximum even when tt is ~1e-11 (tau clamped at 1e-10)
             e[c] = (valid && col < kb_cols) ? expf((__uint_as_float(raw[c]) - st_s[col * 4 + 1]) * st_s[col * 4]) : 0.f;
           }
+          // the exponentials replace the similarities in TMEM: the assignment only needs weight = e / Z
+#pragma unroll
+          for (int c = 0; c < 32; ++c) raw[c] = __float_as_uint(e[c]);
+          tmem_st_32x32(tm_row + ch * 32, raw);
           const float z = warp_col_reduce<false>(e, lane);
           red_s[quad * KP + ch * 32 + lane] = z;
         }
+        tc_wait_st();
         tc_fence_before();
         workers_sync2();
         for (int col = tl; col < kb_cols; col += TOKC)
@@ -535,7 +608,6 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
         workers_sync2();
         tc_fence_after();
         {
-          int j = 0, s = 0;
           float best = -1.f;
           int bi = 0;
 #pragma unroll 1
@@ -543,24 +615,26 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
             if (ch * 32 >= kb_cols) break;
             uint32_t raw[32];
             tmem_ld_32x32(tm_row + ch * 32, raw);
+            const int nc = kb_cols - ch * 32;
             tc_wait_ld();
-            float w32[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {                      // independent exp chains first
-              const int col = min(ch * 32 + c, kb_cols - 1);
-              w32[c] = expf((__uint_as_float(raw[c]) - st_s[col * 4 + 1]) * st_s[col * 4]) * st_s[col * 4 + 2];
-            }
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const int col = ch * 32 + c;
-              if (col < kb_cols) {
-                if (w32[c] > best) { best = w32[c]; bi = s; }   // first maximum wins (torch.argmax)
-                if (++s == p.S) {
-                  idx_s[j * TOKC + tl] = valid ? (int8_t)bi : (int8_t)-1;       // density of the next iteration counts every token
-                  w_s[j * TOKC + tl] = ((boxmask >> j) & 1u) ? best : 0.f;      // masked tokens are zero vectors: they add nothing
-                  if (p.trace && valid) p.trace[((size_t)it * p.n_tot + o0 + j) * p.N + n_tok] = bi;
-                  s = 0; ++j; best = -1.f; bi = 0;
-                }
+              // branch-free running arg-max per instance (first maximum wins, like torch.argmax): restart at the instance's first
+              // column, and write the running result after EVERY column -- the value left behind by the instance's last column is
+              // the final one (no per-instance flush branch in the unrolled loop)
+              const int col = min(ch * 32 + c, kb_cols - 1);
+              const int sidx = cs_s[col], jv = cj_s[col];
+              const float w = __uint_as_float(raw[c]) * st_s[col * 4 + 2];       // e (written by the statistics phase) / Z
+              const bool first = sidx == 0;
+              const float bprev = first ? -1.f : best;
+              const int iprev = first ? 0 : bi;
+              const bool better = w > bprev;
+              best = better ? w : bprev;
+              bi = better ? sidx : iprev;
+              if (c < nc) {
+                idx_s[jv * TOKC + tl] = valid ? (int8_t)bi : (int8_t)-1;          // density of the next iteration counts every token
+                w_s[jv * TOKC + tl] = ((boxmask >> jv) & 1u) ? best : 0.f;        // masked tokens are zero vectors: they add nothing
+                if (p.trace && valid && sidx == p.S - 1) p.trace[((size_t)it * p.n_tot + o0 + jv) * p.N + n_tok] = bi;
               }
             }
           }
@@ -605,11 +679,16 @@ mean_shift_v2_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __grid_c
             if (ch * 32 >= kb_cols) break;
             uint32_t raw[32];
             tmem_ld_32x32(tm_row + TM_UPD + buf * KP + ch * 32, raw);
+            float scl[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) scl[c] = sc_s[(ch * 32 + c) * 2 + 1];
             tc_wait_ld();
+            const int ncol = min(32, kb_cols - ch * 32);
+            float* d = dst + (size_t)(ch * 32) * p.C;           // running pointer: one 64-bit add per row instead of a wide multiply
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const int col = ch * 32 + c;
-              if (col < kb_cols) dst[(size_t)col * p.C] = __uint_as_float(raw[c]) * sc_s[col * 2 + 1];
+              if (c < ncol) *d = __uint_as_float(raw[c]) * scl[c];
+              d += p.C;
             }
           }
           tc_fence_before();
@@ -675,18 +754,41 @@ int kp_for(int kmax, int max_obj) {
   return 0;
 }
 
+int g_v2_plain_launches = 0;
+
 template <int KP>
 int launch_v2(const CUtensorMap* tm, V2Params& p, int num_sms, int G, cudaStream_t stream) {
   const size_t smem = Cfg<KP>::SMEM;
   AS_CUDA(cudaFuncSetAttribute(mean_shift_v2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  AS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mean_shift_v2_kernel<KP>, V2_THREADS, smem));
-  occ = occ < 1 ? 0 : (occ > (512 / Cfg<KP>::TM_COLS) ? 512 / Cfg<KP>::TM_COLS : occ);        // TMEM: 512 columns per SM
+  // without the carve-out preference the driver sizes the shared-memory partition for ONE CTA of this size and the second
+  // CTA of the pair never becomes resident (occupancy 1: seen as a grid of 128 in the first ncu capture)
+  AS_CUDA(cudaFuncSetAttribute(mean_shift_v2_kernel<KP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // Resident CTAs per SM from the hardware limits: shared memory (228 KB per SM, 1 KB reserved per CTA), registers (granted per
+  // 4-warp granule and per SM sub-partition) and TMEM (512 columns).  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
+  // the two-CTA variant although the hardware limits are 2 / 2 (ncu launch__occupancy_limit_{registers,shared_mem} of this very
+  // kernel); cudaLaunchCooperativeKernel applies the same estimate, so when it refuses the grid the kernel is launched plainly --
+  // the grid never exceeds what is resident at once, the stream order guarantees the SMs are free, and the group barrier traps
+  // after 4 s instead of hanging if that assumption were ever violated.
+  cudaFuncAttributes fa;
+  AS_CUDA(cudaFuncGetAttributes(&fa, mean_shift_v2_kernel<KP>));
+  const int warps = (V2_THREADS + 31) / 32;
+  const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+  const int warps_per_subpart = regs_per_warp ? 16384 / regs_per_warp : 64;
+  int occ = (4 * warps_per_subpart) / warps;
+  occ = std::min(occ, (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024)));
+  occ = std::min(occ, 512 / Cfg<KP>::TM_COLS);
   int groups = occ * num_sms / G;
   if (groups < 1) return AS_ERR_BAD_ARG;
   if (groups > p.n_img) groups = p.n_img;
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
-  AS_CUDA(cudaLaunchCooperativeKernel((const void*)mean_shift_v2_kernel<KP>, dim3(groups * G), dim3(V2_THREADS), args, smem, stream));
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)mean_shift_v2_kernel<KP>, dim3(groups * G), dim3(V2_THREADS), args, smem, stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    (void)cudaGetLastError();
+    g_v2_plain_launches++;
+    mean_shift_v2_kernel<KP><<<groups * G, V2_THREADS, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return (int)e;
   return 0;
 }
 
@@ -695,6 +797,21 @@ int launch_v2(const CUtensorMap* tm, V2Params& p, int num_sms, int G, cudaStream
 static unsigned long long* g_v2_dbg = nullptr;
 // profiling aid: device buffer of [grid][16] uint64 that receives the accumulated nanoseconds per phase (null = off)
 extern "C" void as_mean_shift_v2_debug(unsigned long long* buf) { g_v2_dbg = buf; }
+
+// diagnostics: resident CTAs per SM the runtime grants the KP = 64 variant (2 expected), registers, static shared memory
+extern "C" int as_mean_shift_v2_occupancy(int* regs, int* static_smem, int* dyn_smem) {
+  const size_t smem = Cfg<64>::SMEM;
+  cudaFuncSetAttribute(mean_shift_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(mean_shift_v2_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, mean_shift_v2_kernel<64>) != cudaSuccess) return -1;
+  if (regs) *regs = a.numRegs;
+  if (static_smem) *static_smem = (int)a.sharedSizeBytes;
+  if (dyn_smem) *dyn_smem = (int)smem;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mean_shift_v2_kernel<64>, V2_THREADS, smem) != cudaSuccess) return -2;
+  return occ + 100 * g_v2_plain_launches;     // + 100 x launches that had to bypass the cooperative launch's estimate
+}
 
 // 0 when the kernel cannot take the problem (the caller then uses as_mean_shift_tc / as_mean_shift)
 extern "C" int as_mean_shift_v2_supported(int N, int C, int kmax, int max_obj) {
@@ -713,6 +830,7 @@ extern "C" size_t as_mean_shift_v2_workspace(int n_img, int N, int C, int kmax, 
   add((size_t)n_img * G * KP * 4); add((size_t)n_img * G * KP * 8); add((size_t)n_img * G * KP * 4);
   add((size_t)n_img * G * KP * C * 4);                                 // proto partials
   add((size_t)n_img * 4);                                              // barrier counters
+  add((size_t)(2 + 1024) * 4);                                         // scheduling tickets + per-SM arrival counters
   return b;
 }
 
@@ -744,12 +862,22 @@ extern "C" int as_mean_shift_v2(const float* feats, long long feat_img_stride, i
   p.z_part = (float*)take((size_t)n_img * G * KP * 4);
   p.proto_part = (float*)take((size_t)n_img * G * KP * C * 4);
   p.bar = (unsigned*)take((size_t)n_img * 4);
+  p.sched = (unsigned*)take((size_t)(2 + 1024) * 4);
   p.n_img = n_img; p.N = N; p.C = C; p.hp = hp; p.wp = wp; p.S = S; p.G = G; p.n_shift = n_shift; p.clamp0 = clamp0;
   p.tt0 = (float)(temp * tau0); p.temp = (float)temp;
   p.dbg = g_v2_dbg;
+  {
+    static int stagger = -1;                 // env AS_MS_STAGGER_NS: start offset of the second half of the image groups
+    if (stagger < 0) {
+      const char* e = getenv("AS_MS_STAGGER_NS");
+      stagger = e ? atoi(e) : 8000;
+    }
+    p.stagger_ns = (unsigned)stagger;
+  }
   p.img_first = img_first; p.img_nobj = img_nobj; p.rois = rois; p.proto = proto; p.sim_out = sim_out; p.trace = trace; p.n_tot = n_tot;
 
   AS_CUDA(cudaMemsetAsync(p.bar, 0, (size_t)n_img * 4, stream));
+  AS_CUDA(cudaMemsetAsync(p.sched, 0, (size_t)(2 + 1024) * 4, stream));
   AS_CUDA(cudaMemsetAsync(p.phat_hi, 0, (size_t)n_img * KP * C * 2, stream));      // rows past an image's seed count stay zero
   AS_CUDA(cudaMemsetAsync(p.phat_lo, 0, (size_t)n_img * KP * C * 2, stream));
   v2_split_tokens<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, hi, lo, (float*)p.den);

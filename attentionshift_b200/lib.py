@@ -44,6 +44,7 @@ SIGNATURES = {
     'as_mean_shift_v2_supported': (_i, [_i, _i, _i, _i]),
     'as_mean_shift_v2_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_mean_shift_v2_debug': (None, [_vp]),
+    'as_mean_shift_v2_occupancy': (_i, [_vp, _vp, _vp]),
     'as_mean_shift_v2': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
@@ -162,7 +163,7 @@ def load():
             fn = getattr(cdll, name)            # AttributeError here = header / library drift
             fn.restype = res
             fn.argtypes = args
-            setattr(lib, name, fn if name.endswith(('_workspace', '_supported', '_debug')) else TIMERS.wrap(name, fn))
+            setattr(lib, name, fn if name.endswith(('_workspace', '_supported', '_debug', '_occupancy')) else TIMERS.wrap(name, fn))
         _lib = lib
     return _lib
 

@@ -196,7 +196,7 @@ def one_step(bb, head, img_dev, inputs, return_mask):
     out = bb(img_dev)
     hp, wp = img_dev.shape[-2] // 16, img_dev.shape[-1] // 16
     vit_feat = out['last_feat'][:, 1:]                                   # token-major [B,N,C] view (DET:77 without the transpose)
-    res = head.seed_pseudo_gt(out['feature'], None, None, None, None, vit_feat=vit_feat.unflatten(1, (hp, wp)).permute(0, 3, 1, 2),
+    res = head.seed_pseudo_gt(None, None, None, None, None, vit_feat=vit_feat.unflatten(1, (hp, wp)).permute(0, 3, 1, 2),
                               point_cls=out['outputs_class'], point_reg=out['outputs_coord'], attns=out['attns'],
                               gt_points=gt_points, gt_points_labels=labels, return_mask=return_mask, pos_mask_thr=0.6,
                               neg_mask_thr=0.1, num_mask_point_gt=10, corr_size=21, obj_tau=0.85, pos_inds=pos_inds,

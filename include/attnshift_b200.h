@@ -194,6 +194,8 @@ int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img
 int as_mean_shift_v2_supported(int N, int C, int kmax, int max_obj);
 size_t as_mean_shift_v2_workspace(int n_img, int N, int C, int kmax, int max_obj);
 void as_mean_shift_v2_debug(unsigned long long* buf);
+/* diagnostics: resident CTAs per SM granted to the <= 64-column variant (2 expected), its registers / static / dynamic smem */
+int as_mean_shift_v2_occupancy(int* regs, int* static_smem, int* dyn_smem);
 int as_mean_shift_v2(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
                      const int* img_first, const int* img_nobj, int kmax, int max_obj, const float* rois, int n_tot, int S,
                      float* proto, float* sim_out, int n_shift, double tau0, double temp, int clamp0, int* trace,

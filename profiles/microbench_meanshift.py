@@ -34,11 +34,26 @@ def timeit(fn, n=10):
 
 
 b_alg = ((iters + 1) * N * C * 4 + n_obj * S * N * 4 + 2 * n_obj * S * C * 4) * n_img
-for impl in ('fused', 'tc', 'fp32'):
+for impl in ('v2', 'fused', 'tc', 'fp32'):
     ms = timeit(lambda: ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, iters, n_per_img=npi, impl=impl))
     print(f'{impl:6s} {ms:8.3f} ms   B_alg {b_alg / 1e6:.1f} MB -> {b_alg / ms / 1e6:8.1f} GB/s')
 
 L = lib.load()
+# ---- per-phase nanoseconds of the second-generation persistent kernel (256 CTAs of 128 tokens, two per SM)
+G2 = ((N + 63) // 64 + 1) // 2
+dbg2 = torch.zeros(n_img * G2 * 16, dtype=torch.int64, device=dev)
+L.as_mean_shift_v2_debug(lib.ptr(dbg2))
+ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, iters, n_per_img=npi, impl='v2')
+torch.cuda.synchronize()
+L.as_mean_shift_v2_debug(None)
+d2 = dbg2.view(n_img * G2, 16).double() / 1e3
+names2 = ['0 seeds p^ + barrier', '1 affinity epilogue + column stats', '2 barrier 1', '3 statistics / partial Z', '4 barrier 2',
+          '5 assign + weight tiles', '6 update (tcgen05) + epilogue', '7 barrier 3', '8 reduce', '9 barrier 4', '10 affinity main loop (TMA + tcgen05)']
+print('v2 phase                           mean us   max us   (worker thread 0 of each CTA, summed over the call)')
+for k, nme in enumerate(names2):
+    print(f'{nme:34s} {d2[:, k].mean().item():8.1f} {d2[:, k].max().item():8.1f}')
+print('v2 total', d2.sum(1).mean().item())
+
 dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 L.as_mean_shift_fused_debug(lib.ptr(dbg))
 ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, iters, n_per_img=npi, impl='fused')

@@ -21,9 +21,13 @@ for _ in range(2):
         ops.linear_f16(x768, w_fc1, b3072, ops.EPI_GELU_F16)
     elif which == 'qkv':
         ops.qkv_proj(x768, w_qkv, b2304, B, T, H, Tpad)
-    elif which in ('mhsa', 'headmean'):
+    elif which in ('mhsa', 'headmean', 'headmean_lean', 'headmean_rows'):
         q, k, vt = ops.qkv_proj(x768, w_qkv, b2304, B, T, H, Tpad)
         o, m, l = ops.mhsa_fwd(q, k, vt, T)
-        if which == 'headmean':
+        if which == 'headmean':            # reference-shaped production: fp32 map + transposed pair + row sums
             ops.attn_headmean(q, k, m, l, T)
+        elif which == 'headmean_lean':     # roll-out operand only (every layer but the last, attn_format='rollout')
+            ops.attn_headmean(q, k, m, l, T, want_map=False)
+        elif which == 'headmean_rows':     # the last layer: point-token rows only
+            ops.attn_headmean(q, k, m, l, T, want_transposed=False, row0=T - 100)
 torch.cuda.synchronize()

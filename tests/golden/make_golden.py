@@ -134,9 +134,30 @@ def vit_case(embed, heads, depth, img, n_pt, seed):
                 point_tokens=out['point_tokens'].clone())
 
 
+def mil_case(seed=3):
+    """MAEBoxHeadMIL (mae_bbox_head_mil.py:140-169), the reference class itself: parameters, RoI features in, layer choice and
+    MIL loss out (mmcv's RoIAlign is absent here, so the golden starts at the RoI features)."""
+    Ref = ref_loader.load_mil_head()
+    cfg = dict(in_channels=48, img_size=224, patch_size=16, embed_dim=32, depth=4, num_heads=8, mlp_ratio=4., num_classes=20,
+               num_layers_query=7, loss_mil_factor=1.0, hidden_dim=64, roi_size=7)
+    torch.manual_seed(seed)
+    ref = Ref(pretrained=True, use_checkpoint=False, **cfg).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    n_inst = 6
+    x = torch.randn(n_inst * 7, 48, 7, 7, generator=g)
+    labels = [torch.tensor([3, 19, 0]), torch.tensor([7, 7, 11])]
+    with torch.no_grad():
+        idx, loss = ref(x.clone(), gt_labels=[l.clone() for l in labels])
+    return dict(cfg=cfg, state_dict={k: v.clone() for k, v in ref.state_dict().items()}, x=x, labels=labels, gt_index=idx, mil_loss=loss)
+
+
 if __name__ == '__main__':
     assert ref_loader.available(), 'needs /root/reference'
     torch.set_num_threads(8)
+    if '--only-mil' in sys.argv:
+        torch.save(mil_case(), os.path.join(OUT, 'mil_head.pt'))
+        print('mil_head.pt', os.path.getsize(os.path.join(OUT, 'mil_head.pt')))
+        sys.exit(0)
     torch.save(attnshift_case(14, 32, 2, scene_seed=11, rng_seed=5, noise=0.3, n_shift=5, keep_maps=True),
                os.path.join(OUT, 'attnshift_224_c32.pt'))
     torch.save(attnshift_case(28, 64, 3, scene_seed=3, rng_seed=7, noise=0.4, n_shift=10, keep_maps=False),
@@ -145,6 +166,7 @@ if __name__ == '__main__':
     torch.save(assigner_case(), os.path.join(OUT, 'point_assigner.pt'))
     torch.save(rollout_case(t=61, layers=7, b=2, seed=1), os.path.join(OUT, 'rollout_t61.pt'))
     torch.save(vit_case(embed=128, heads=2, depth=2, img=64, n_pt=12, seed=0), os.path.join(OUT, 'vit_e128_d2.pt'))
+    torch.save(mil_case(), os.path.join(OUT, 'mil_head.pt'))
     for f in sorted(os.listdir(OUT)):
         if f.endswith('.pt'):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -127,11 +127,30 @@ def test_fused_matches_tc_multi_image(n_img, hp, c, S, kernel):
         out[impl] = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, 4, want_trace=True, n_per_img=n_per_img, impl=impl)
     torch.cuda.synchronize()
     (p_a, s_a, t_a), (p_b, s_b, t_b) = out['tc'], out[kernel]
-    agree = (t_a == t_b).float().mean().item()
-    assert agree > 0.999, agree
-    scale = p_a.abs().max().item()
-    assert (p_a - p_b).abs().max().item() <= 2e-3 * scale
-    assert (s_a - s_b).abs().max().item() <= 2e-3
+    # both against the oracle, image by image (the batch is ragged: every image has its own instance count).  An arg-max decided
+    # at rounding level (see test_mean_shift_vs_oracle) legitimately moves a token to another seed and with it that seed's
+    # prototype, so prototypes / maps are compared on the images whose hard assignments all equal the oracle's, and the flips are
+    # counted (and bounded) on the others.
+    o0, flips, clean = 0, {'tc': 0, kernel: 0}, {'tc': 0, kernel: 0}
+    for i, (sc, n) in enumerate(zip(scenes, n_per_img)):
+        m_i = torch.stack([((sc['labels'] == 2 * j + 1) | (sc['labels'] == 2 * j + 2)).float() for j in range(n)])
+        tr = []
+        o_prot, o_sim = O.mean_shift_from_maps(m_i, sc['vit_feat'], sc['rois'], n_shift=4, n_points=S, trace=tr)
+        want = torch.stack(tr)                                                       # [n_shift, n, N]
+        for name, (pp, ss, tt) in (('tc', (p_a, s_a, t_a)), (kernel, (p_b, s_b, t_b))):
+            nf = int((tt[:, o0:o0 + n].cpu().long() != want).sum())
+            flips[name] += nf
+            if nf == 0:
+                clean[name] += 1
+                torch.testing.assert_close(pp[o0:o0 + n].cpu().flatten(0, 1), o_prot, rtol=1e-3, atol=1e-4 * o_prot.abs().max().item(),
+                                           msg=lambda m, name=name, i=i: f'{name}, image {i}: prototypes vs oracle: {m}')
+                torch.testing.assert_close(ss[o0:o0 + n].cpu().unflatten(-1, (hp, hp)).flatten(0, 1), o_sim, rtol=1e-3, atol=1e-4,
+                                           msg=lambda m, name=name, i=i: f'{name}, image {i}: similarity maps vs oracle: {m}')
+        o0 += n
+    total = 4 * sum(n_per_img) * N
+    print(f'multi-image mean shift vs oracle: arg-max flips {flips} of {total} assignments; images with none: {clean} of {n_img}')
+    for name in flips:
+        assert flips[name] <= 0.002 * total + 2 and clean[name] >= (n_img + 1) // 2, (flips, clean)
     # run-to-run determinism of the ordered reductions
     again = ops.mean_shift(proto0, feats, obj_img, rois, hp, hp, 4, want_trace=True, n_per_img=n_per_img, impl=kernel)
     assert torch.equal(again[0], p_b) and torch.equal(again[1], s_b) and torch.equal(again[2], t_b)
