@@ -124,7 +124,8 @@ class VisionTransformerDet(nn.Module):
                  recompute_last_feat=False, point_tokens_num=100, num_classes=20, return_attention=False,
                  with_point_head=True, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=None, init_values=0,
-                 attn_layers=None, attn_format='full', cuda_graph=False, allow_detached_training=False, **kwargs):
+                 attn_layers=None, attn_format='full', cuda_graph=False, allow_detached_training=False, train_backward=True,
+                 **kwargs):
         super().__init__()
         assert not with_fpn or (patch_size in (8, 16))
         assert not recompute_last_feat or (last_feat and recompute_last_feat)
@@ -166,6 +167,8 @@ class VisionTransformerDet(nn.Module):
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
         self.allow_detached_training = bool(allow_detached_training)
+        # training mode + autograd + trainable parameters -> the autograd forward of training.py (device kernels in both directions)
+        self.train_backward = bool(train_backward)
 
         self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
         num_patches = self.patch_embed.num_patches
@@ -302,20 +305,69 @@ class VisionTransformerDet(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _check_no_training(self):
-        """The device path is a forward pass without a backward (attention-shift consumes detached tensors, DET:77).  Called
+        """(Only reached with ``train_backward=False`` or a host tensor.)  The inference path is a forward pass without a backward (attention-shift consumes detached tensors, DET:77).  Called
         in training mode with autograd on and trainable parameters it would silently return constants to the optimiser -- the
         backbone would never train and the point losses would have no gradient path -- so it refuses instead."""
         if self.training and torch.is_grad_enabled() and not self.allow_detached_training and \
                 any(p.requires_grad for p in self.parameters()):
             raise RuntimeError(
-                'attentionshift_b200.VisionTransformerDet is forward-only (no backward kernels): it cannot train its parameters. '
+                'attentionshift_b200.VisionTransformerDet: this forward is forward-only (train_backward=False or a host tensor): it cannot train its parameters. '
                 'Use it under torch.no_grad() / .eval() (pseudo-label generation, inference), freeze it (frozen_stages, '
                 'requires_grad_(False)), keep the reference backbone for the trained copy, or pass allow_detached_training=True '
                 'to accept outputs that are detached from the parameters.')
 
     def forward(self, x):           # VTD:221-275
+        if self.training and torch.is_grad_enabled() and self.train_backward and x.is_cuda and \
+                any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(x)
         self._check_no_training()
         return self._forward_no_grad(x)
+
+    def _forward_train(self, x):
+        """Training forward with autograd (``training.py``): the GEMMs and the attention run on the device kernels in both
+        directions, LayerNorm / GELU / residual adds are torch ops.  Same return dict; the head-mean maps are detached (the
+        attention-shift head consumes them without gradient, DET:77 / RH:2356).  drop_rate / drop_path_rate are not applied."""
+        from . import training as TR
+        B, _, H, W = x.shape
+        Hp, Wp = H // self.patch_size, W // self.patch_size
+        N, C = Hp * Wp, self.embed_dim
+        with torch.no_grad():
+            cols = ops.patch_im2col_f16(x.contiguous().float())
+        emb = TR.LinearFn.apply(cols, self.patch_embed.proj.weight.view(C, -1), self.patch_embed.proj.bias, True).view(B, N, C)
+        pos = self.interpolate_pos_encoding(N, H, W)
+        tok = torch.cat((self.cls_token.expand(B, -1, -1) + pos[:, :1], emb + pos[:, 1:],
+                         (self.point_token + self.point_pos_embed).expand(B, -1, -1)), dim=1)      # VTD:203-213
+        T = tok.shape[1]
+        xs = tok.reshape(B * T, C)
+        depth = len(self.blocks)
+        first_attn = 0 if self.attn_layers is None else depth - int(self.attn_layers)
+        features, attns = [], []
+        Tp = self.point_tokens_num
+        for i in range(depth):
+            want = self.return_attention and i >= first_attn
+            kw = None
+            if want and self.attn_format == 'rollout':
+                kw = dict(want_transposed=False, row0=T - Tp) if i == depth - 1 else dict(want_map=False)
+            xs, a = TR.block_forward(self.blocks[i], xs, B, T, self.num_heads, want, kw)
+            if self.return_attention:
+                attns.append(a)
+            if i in self.out_indices:
+                features.append(xs.view(B, T, C)[:, 1:-Tp].permute(0, 2, 1).reshape(B, C, Hp, Wp))
+        xo = xs.view(B, T, C)
+        point_tokens = xo[:, -Tp:]
+        ret = dict(org_feats=torch.stack(features, dim=1) if features else None, point_tokens=point_tokens)
+        if self.with_fpn:
+            fops = [self.fpn1, self.fpn2, self.fpn3, self.fpn4]
+            features = [fops[j](f) for j, f in enumerate(features)]
+        ret['feature'] = tuple(features)
+        if self.with_point_head:
+            ret['outputs_class'] = self.class_embed(point_tokens)
+            ret['outputs_coord'] = self.bbox_embed(point_tokens).sigmoid()
+        if self.return_attention and self.last_feat:
+            ret['attns'] = attns
+        if self.last_feat:
+            ret['last_feat'] = xo[:, :-Tp]
+        return ret
 
     @torch.no_grad()
     def _forward_no_grad(self, x):

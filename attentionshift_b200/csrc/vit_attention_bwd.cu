@@ -1,0 +1,402 @@
+// Attention backward on tcgen05 (what DDP training of the backbone needs; reference forward VT:74-86, whose
+// backward torch autograd derives from the materialised [B,h,T,T] matrix).  Flash-style: nothing of size T x T is stored; the
+// probabilities are recomputed from (Q, K, m, l) exactly as the head-mean pass does: P = exp2(c * QK^T - m) / l.
+//
+//   dV = P^T dO          dP = dO V^T          delta_i = sum_d dO_id O_id          dS = P o (dP - delta) * scale
+//   dK = dS^T Q          dQ = dS K
+//
+// Two kernels, both deterministic (no atomics): as_mhsa_bwd_dkv keeps one 128-key tile (K_j, V_j) resident and walks the query
+// tiles, accumulating dK_j / dV_j in TMEM; as_mhsa_bwd_dq keeps one 128-query tile (Q_i, dO_i) resident, walks the key tiles and
+// accumulates dQ_i in TMEM.  Per tile pair: S and dP on the tensor cores into TMEM, four softmax warps (thread = query row = TMEM
+// lane) turn them into P and dS (fp16, written into shared memory in the 128-byte-swizzled operand layout), and the tensor
+// cores consume those tiles straight from shared memory -- as an MN-major A operand for the transposed products (P^T, dS^T),
+// K-major for dS K.  All B operands are K-major: the host passes Q^T, dO^T, K^T ([BH, 64, Tpad], like the forward's V^T) next
+// to the row-major tensors.
+#include "common.cuh"
+
+using namespace asb;
+
+namespace {
+
+constexpr int BT = 128, HD = 64;
+constexpr int TILE = BT * HD * 2;          // 16 KB: [128 rows x 64 halves], or a transposed tile as two [64 x 64] boxes
+constexpr int PTILE = BT * BT * 2;         // 32 KB: [128 q x 128 k] fp16 as two 64-column blocks of 16 KB
+constexpr int BWD_THREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2-5 softmax (TMEM lane quadrant = warp & 3)
+constexpr uint32_t C_S = 0, C_DP = 128, C_ACC0 = 256, C_ACC1 = 320;
+
+struct BwdParams {
+  int T, heads, nt;                        // nt = ceil(T / 128)
+  float scale_log2, scale;                 // head_dim^-0.5 * log2(e), head_dim^-0.5
+  const float* m;                          // [BH, T] softmax offsets of the forward (log2 domain)
+  const float* l;                          // [BH, T] softmax denominators
+  const float* delta;                      // [BH, T] rowsum(dO o O)
+  float* out0;                             // dkv: dK [BH, T, 64];  dq: dQ [BH, T, 64]
+  float* out1;                             // dkv: dV [BH, T, 64]
+};
+
+__device__ __forceinline__ int sw128p(int row, int col) {      // byte offset of (row, col) in a [rows x 64 halves] swizzled block
+  return row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
+}
+__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// P and dS of one (query tile, key tile) pair from the S / dP accumulators of this thread's query row.
+// want_p: also write P (the dkv kernel needs both tiles, the dq kernel only dS).
+template <bool kWantP>
+__device__ __forceinline__ void make_p_ds(uint32_t tm_row, uint8_t* p_s, uint8_t* ds_s, int row, bool row_ok, int k0, int T,
+                                          float c, float scale, float mi, float inv_l, float di) {
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t s[32], dp[32];
+    tmem_ld_32x32(tm_row + C_S + ch * 32, s);
+    tmem_ld_32x32(tm_row + C_DP + ch * 32, dp);
+    tc_wait_ld();
+    uint32_t pw[16], dw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float pv[2], dv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = ch * 32 + 2 * i + e;
+        const bool ok = row_ok && (k0 + col < T);
+        const float p = ok ? ex2_approx(fmaf(__uint_as_float(s[2 * i + e]), c, -mi)) * inv_l : 0.f;
+        pv[e] = p;
+        dv[e] = p * (__uint_as_float(dp[2 * i + e]) - di) * scale;
+      }
+      const __half2 ph = __floats2half2_rn(pv[0], pv[1]), dh = __floats2half2_rn(dv[0], dv[1]);
+      pw[i] = *reinterpret_cast<const uint32_t*>(&ph);
+      dw[i] = *reinterpret_cast<const uint32_t*>(&dh);
+    }
+    // 32 columns = 64 bytes = four 16-byte chunks of the row's 128-byte swizzled line in block (ch / 2)
+    const int blk = ch >> 1, cbase = (ch & 1) * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int off = blk * (PTILE / 2) + sw128p(row, cbase + g * 8);
+      if (kWantP) *reinterpret_cast<uint4*>(p_s + off) = make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
+      *reinterpret_cast<uint4*>(ds_s + off) = make_uint4(dw[4 * g], dw[4 * g + 1], dw[4 * g + 2], dw[4 * g + 3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dK, dV: one key tile per CTA, loop over the query tiles
+constexpr int DKV_STAGE = 4 * TILE;                                   // Q_i, dO_i, Q^T_i, dO^T_i
+constexpr int DKV_SMEM = 1024 + 2 * TILE + 2 * DKV_STAGE + 2 * PTILE + 256;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_qt, const __grid_constant__ CUtensorMap tm_dot, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* k_s = smem;                       // [128 k x 64 d]
+  uint8_t* v_s = smem + TILE;                // [128 k x 64 d]
+  uint8_t* ring = smem + 2 * TILE;           // 2 stages
+  uint8_t* p_s = ring + 2 * DKV_STAGE;       // P  [128 q x 128 k]
+  uint8_t* ds_s = p_s + PTILE;               // dS [128 q x 128 k]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + PTILE);
+  uint64_t* kv_full = bars;                  // 1
+  uint64_t* full = bars + 1;                 // 2
+  uint64_t* empty = bars + 3;                // 2
+  uint64_t* s_full = bars + 5;               // S, dP ready (commit)
+  uint64_t* s_free = bars + 6;               // S, dP read (4 warps)
+  uint64_t* p_full = bars + 7;               // P, dS written (4 warps)
+  uint64_t* p_free = bars + 8;               // P, dS consumed (commit)
+  uint64_t* acc_full = bars + 9;             // all MMAs done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, bh = blockIdx.z * p.heads + blockIdx.y;
+  const int k0 = jt * BT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_dot);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(p_free, 1); mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TILE);
+      tma_load_3d(k_s, &tm_k, kv_full, 0, k0, bh);
+      tma_load_3d(v_s, &tm_v, kv_full, 0, k0, bh);
+      for (int it = 0; it < p.nt; ++it) {
+        const int st = it & 1;
+        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], DKV_STAGE);
+        uint8_t* d = ring + st * DKV_STAGE;
+        tma_load_3d(d, &tm_q, &full[st], 0, it * BT, bh);
+        tma_load_3d(d + TILE, &tm_do, &full[st], 0, it * BT, bh);
+        tma_load_3d(d + 2 * TILE, &tm_qt, &full[st], it * BT, 0, bh);
+        tma_load_3d(d + 2 * TILE + TILE / 2, &tm_qt, &full[st], it * BT + 64, 0, bh);
+        tma_load_3d(d + 3 * TILE, &tm_dot, &full[st], it * BT, 0, bh);
+        tma_load_3d(d + 3 * TILE + TILE / 2, &tm_dot, &full[st], it * BT + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BT, BT);                       // S, dP: M = 128 q, N = 128 k
+    constexpr uint32_t idesc_t = umma_idesc(0, BT, HD) | (1u << 15);          // dV, dK: M = 128 k (A MN-major), N = 64 d
+    mbar_wait(kv_full, 0);
+    for (int it = 0; it < p.nt; ++it) {
+      const int st = it & 1;
+      mbar_wait(&full[st], (it >> 1) & 1);
+      mbar_wait(s_free, (it & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t q_a = smem_u32(ring + st * DKV_STAGE), do_a = q_a + TILE, qt_a = q_a + 2 * TILE, dot_a = q_a + 3 * TILE;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + C_S, umma_desc_k_sw128(q_a + k * 32), umma_desc_k_sw128(smem_u32(k_s) + k * 32), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + C_DP, umma_desc_k_sw128(do_a + k * 32), umma_desc_k_sw128(smem_u32(v_s) + k * 32), idesc_s, k != 0);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, it & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t pa = smem_u32(p_s), da = smem_u32(ds_s);
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k) {                    // K = 16 query rows per MMA
+          const uint32_t boff = (k >> 2) * (TILE / 2) + (k & 3) * 32;   // transposed tiles: two [64 d x 64 q] boxes
+          mma_f16_ss(tmem + C_ACC1, umma_desc_mn_sw128(pa + k * 2048, PTILE / 2), umma_desc_k_sw128(dot_a + boff), idesc_t, (it | k) != 0);
+          mma_f16_ss(tmem + C_ACC0, umma_desc_mn_sw128(da + k * 2048, PTILE / 2), umma_desc_k_sw128(qt_a + boff), idesc_t, (it | k) != 0);
+        }
+        tc_commit(&empty[st]);
+        tc_commit(p_free);
+        if (it == p.nt - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+    for (int it = 0; it < p.nt; ++it) {
+      const int t = it * BT + row;
+      const bool ok = t < p.T;
+      const size_t si = (size_t)bh * p.T + (ok ? t : 0);
+      const float mi = p.m[si], inv_l = 1.f / p.l[si], di = p.delta[si];
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      mbar_wait(p_free, (it & 1) ^ 1);                          // the previous tile's P / dS have been consumed
+      make_p_ds<true>(tm_row, p_s, ds_s, row, ok, k0, p.T, p.scale_log2, p.scale, mi, inv_l, di);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+    }
+    // epilogue: thread = key row
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int kr = k0 + row;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t a[32], b[32];
+      tmem_ld_32x32(tm_row + C_ACC0 + half * 32, a);
+      tmem_ld_32x32(tm_row + C_ACC1 + half * 32, b);
+      tc_wait_ld();
+      if (kr < p.T) {
+        float4* dk = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + kr) * HD + half * 32);
+        float4* dv = reinterpret_cast<float4*>(p.out1 + ((size_t)bh * p.T + kr) * HD + half * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          dk[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+          dv[g] = make_float4(__uint_as_float(b[4 * g]), __uint_as_float(b[4 * g + 1]), __uint_as_float(b[4 * g + 2]), __uint_as_float(b[4 * g + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------ dQ: one query tile per CTA, loop over the key tiles
+constexpr int DQ_STAGE = 3 * TILE;                                    // K_j, V_j, K^T_j
+constexpr int DQ_SMEM = 1024 + 2 * TILE + 2 * DQ_STAGE + PTILE + 256;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_kt, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* do_s = smem + TILE;
+  uint8_t* ring = smem + 2 * TILE;
+  uint8_t* ds_s = ring + 2 * DQ_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + PTILE);
+  uint64_t* q_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* empty = bars + 3;
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_free = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* p_free = bars + 8;
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, bh = blockIdx.z * p.heads + blockIdx.y;
+  const int q0 = qt * BT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_kt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(p_free, 1); mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE);
+      tma_load_3d(q_s, &tm_q, q_full, 0, q0, bh);
+      tma_load_3d(do_s, &tm_do, q_full, 0, q0, bh);
+      for (int it = 0; it < p.nt; ++it) {
+        const int st = it & 1;
+        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], DQ_STAGE);
+        uint8_t* d = ring + st * DQ_STAGE;
+        tma_load_3d(d, &tm_k, &full[st], 0, it * BT, bh);
+        tma_load_3d(d + TILE, &tm_v, &full[st], 0, it * BT, bh);
+        tma_load_3d(d + 2 * TILE, &tm_kt, &full[st], it * BT, 0, bh);
+        tma_load_3d(d + 2 * TILE + TILE / 2, &tm_kt, &full[st], it * BT + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(0, BT, BT);
+    constexpr uint32_t idesc_q = umma_idesc(0, BT, HD);                       // dQ: M = 128 q, N = 64 d, both K-major
+    mbar_wait(q_full, 0);
+    for (int it = 0; it < p.nt; ++it) {
+      const int st = it & 1;
+      mbar_wait(&full[st], (it >> 1) & 1);
+      mbar_wait(s_free, (it & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t k_a = smem_u32(ring + st * DQ_STAGE), v_a = k_a + TILE, kt_a = k_a + 2 * TILE;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + C_S, umma_desc_k_sw128(smem_u32(q_s) + k * 32), umma_desc_k_sw128(k_a + k * 32), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_f16_ss(tmem + C_DP, umma_desc_k_sw128(smem_u32(do_s) + k * 32), umma_desc_k_sw128(v_a + k * 32), idesc_s, k != 0);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, it & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t da = smem_u32(ds_s);
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k) {                    // K = 16 keys per MMA
+          const uint32_t aoff = (k >> 2) * (PTILE / 2) + (k & 3) * 32;
+          const uint32_t boff = (k >> 2) * (TILE / 2) + (k & 3) * 32;
+          mma_f16_ss(tmem + C_ACC0, umma_desc_k_sw128(da + aoff), umma_desc_k_sw128(kt_a + boff), idesc_q, (it | k) != 0);
+        }
+        tc_commit(&empty[st]);
+        tc_commit(p_free);
+        if (it == p.nt - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+    const int t = q0 + row;
+    const bool ok = t < p.T;
+    const size_t si = (size_t)bh * p.T + (ok ? t : 0);
+    const float mi = p.m[si], inv_l = 1.f / p.l[si], di = p.delta[si];
+    for (int it = 0; it < p.nt; ++it) {
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      mbar_wait(p_free, (it & 1) ^ 1);
+      make_p_ds<false>(tm_row, nullptr, ds_s, row, ok, it * BT, p.T, p.scale_log2, p.scale, mi, inv_l, di);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t a[32];
+      tmem_ld_32x32(tm_row + C_ACC0 + half * 32, a);
+      tc_wait_ld();
+      if (ok) {
+        float4* dq = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + t) * HD + half * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dq[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+int enc_rows(CUtensorMap* tm, const void* base, int BH, int T) {           // [BH, T, 64] fp16, box 128 rows
+  uint64_t dims[3] = {HD, (uint64_t)T, (uint64_t)BH};
+  uint64_t str[2] = {HD * 2, (uint64_t)T * HD * 2};
+  uint32_t box[3] = {HD, BT, 1};
+  return as_encode_tmap(tm, base, 2, 3, dims, str, box);
+}
+int enc_transposed(CUtensorMap* tm, const void* base, int BH, int Tpad) {  // [BH, 64, Tpad] fp16, box [64 rows x 64 cols]
+  uint64_t dims[3] = {(uint64_t)Tpad, HD, (uint64_t)BH};
+  uint64_t str[2] = {(uint64_t)Tpad * 2, (uint64_t)Tpad * HD * 2};
+  uint32_t box[3] = {64, HD, 1};
+  return as_encode_tmap(tm, base, 2, 3, dims, str, box);
+}
+
+}  // namespace
+
+// Backward of as_mhsa_fwd.  q, k, v, d_o: [B, heads, T, 64] fp16 (head-major rows); qt, kt, dot: the same tensors transposed,
+// [B, heads, 64, Tpad] fp16 with zero padding (Tpad = T rounded up to 128); m, l: the forward's row statistics [B, heads, T];
+// delta [B, heads, T] = rowsum(dO o O).  Outputs dq, dk, dv [B, heads, T, 64] fp32 (gradients w.r.t. the UNSCALED q, k: the
+// head_dim^-0.5 factor of VT:79 is applied inside).
+extern "C" int as_mhsa_bwd(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                           const void* dot, const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv,
+                           int B, int T, int Tpad, int heads, cudaStream_t stream) {
+  if (Tpad % BT || Tpad < T || T < 1) return AS_ERR_BAD_ARG;
+  const int BH = B * heads;
+  CUtensorMap tq, tk, tv, tdo, tqt, tkt, tdot;
+  int r = enc_rows(&tq, q, BH, T);
+  if (!r) r = enc_rows(&tk, k, BH, T);
+  if (!r) r = enc_rows(&tv, v, BH, T);
+  if (!r) r = enc_rows(&tdo, d_o, BH, T);
+  if (!r) r = enc_transposed(&tqt, qt, BH, Tpad);
+  if (!r) r = enc_transposed(&tkt, kt, BH, Tpad);
+  if (!r) r = enc_transposed(&tdot, dot, BH, Tpad);
+  if (r) return r;
+  static bool attr = false;
+  if (!attr) {
+    AS_CUDA(cudaFuncSetAttribute(mhsa_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    AS_CUDA(cudaFuncSetAttribute(mhsa_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    attr = true;
+  }
+  BwdParams p;
+  p.T = T; p.heads = heads; p.nt = (T + BT - 1) / BT;
+  p.scale = 0.125f; p.scale_log2 = (float)(0.125 * 1.4426950408889634);
+  p.m = m; p.l = l; p.delta = delta;
+  const dim3 grid(p.nt, heads, B);
+  p.out0 = dk; p.out1 = dv;
+  mhsa_bwd_dkv_kernel<<<grid, BWD_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tqt, tdot, p);
+  p.out0 = dq; p.out1 = nullptr;
+  mhsa_bwd_dq_kernel<<<grid, BWD_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, tkt, p);
+  AS_LAUNCH_CHECK();
+  return 0;
+}

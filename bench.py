@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index, period=0.25):
+    def __init__(self, index, period=0.5):
         super().__init__(daemon=True)
         self.index = index
         self.period = period
@@ -227,15 +227,19 @@ def count_launches(fn):
         return None, None
 
 
-def time_steps(fn, steps, barrier):
+def time_steps(fn, steps, barrier, per_step=None):
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream.  ``per_step``: list that
+    receives the individual step times (an event after every step: no synchronisation, the timed region is unchanged)."""
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        evs[i + 1].record()
     barrier()
-    return e0.elapsed_time(e1) / steps
+    if per_step is not None:
+        per_step.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    return evs[0].elapsed_time(evs[steps]) / steps
 
 
 def run_ours(args):
@@ -264,6 +268,8 @@ def run_ours(args):
     # the clock sampler starts BEFORE the warm-up: the first NVML queries of a process are slow and take a driver lock that
     # stalls kernel launches (seen as a 100+ ms hiccup in whichever loop ran first); its samples are reset when timing starts
     sampler = ClockSampler(local) if rank == 0 else None     # one per job: NVML calls serialise on a driver lock shared by all ranks
+    if os.environ.get('AS_BENCH_NO_SAMPLER'):
+        sampler = None                                       # diagnosis only: a line without `clocks` is not a valid bench line
     if sampler is not None:
         sampler.start()
     warm = max(args.warmup, 3)
@@ -274,7 +280,8 @@ def run_ours(args):
     # ---- device-resident timing (value): library timing slots OFF, nothing but the step's own work on the stream
     if sampler is not None:
         sampler.rows = []
-    ms_dev = time_steps(lambda: one_step(bb, head, img_dev, inputs, False), args.steps, barrier)
+    step_ms = []
+    ms_dev = time_steps(lambda: one_step(bb, head, img_dev, inputs, False), args.steps, barrier, step_ms)
 
     # ---- end-to-end timing (e2e): pinned host image -> device every step, masks back to the host every step.
     # The copy of step i+1 runs on a side stream while step i computes (double buffer); every copy is inside the timed region.
@@ -391,7 +398,8 @@ def run_ours(args):
                          peak_source=pk['src'], ms_per_call=round(msf['ms'] / msf['n'], 4), algorithmic_bytes=int(b_alg))
         line = dict(metric='images/sec at 1024^2 bs8 ViT-B attn-shift' if args.config == 'cfg2' else 'images/sec, ' + cfg['name'],
                     value=round(world * B / (ms_dev * 1e-3), 2), unit='images/s',
-                    n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=round(ms_dev, 3), higher_is_better=True,
+                    n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=round(ms_dev, 3), step_ms=[round(v, 2) for v in step_ms],
+                    higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f16 operands / f32 accumulate (ViT GEMMs + attention), f32 (attention shift)',
                     data='synthetic (random-init ViT weights, randn images, random GT points)',
                     config=dict(workload=cfg['name'], per_gpu_batch=B, mode='forward-only, no collective (every rank runs its own batch)',
@@ -401,7 +409,7 @@ def run_ours(args):
                                 kernel_times='library timing slots, separate untimed pass after the timed regions', small=bool(args.small)),
                     e2e=dict(value=round(world * B / (ms_e2e * 1e-3), 2), unit='images/s', ms_per_step=round(ms_e2e, 3),
                              h2d_bytes_per_step=int(img_host.nbytes), d2h_bytes_per_step=int(d2h)),
-                    gpu_launches=n_ours, all_launches=n_all, clocks=sampler.summary(), roofline=roof, roofline_attnshift=roof2,
+                    gpu_launches=n_ours, all_launches=n_all, clocks=sampler.summary() if sampler is not None else None, roofline=roof, roofline_attnshift=roof2,
                     reference_config=ref_cfg,
                     kernel_ms_per_step={k: round(v['ms'], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])})
         if not args.no_cpu_baseline and world == 1:

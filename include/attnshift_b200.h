@@ -52,6 +52,16 @@ int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m,
    exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
 int as_mhsa_set_variant(int variant);
 
+/* Backward of as_mhsa_fwd (what torch autograd derives from VT:79-83 in the reference; needed for DDP training of the
+ * backbone, mmdet/apis/train.py:96-100).  Flash style on tcgen05: P is recomputed from (q, k, m, l), nothing of size T x T is
+ * stored; two deterministic kernels (dK / dV with a resident key tile, dQ with a resident query tile).
+ * q, k, v, d_o [B,heads,T,64] f16 (head-major rows); qt, kt, dot: the same tensors transposed and zero padded, [B,heads,64,Tpad]
+ * (Tpad = T rounded up to 128); m, l [B,heads,T] as written by as_mhsa_fwd; delta [B,heads,T] = rowsum(dO o O).
+ * dq, dk, dv [B,heads,T,64] f32, gradients w.r.t. the unscaled q, k (the head_dim^-0.5 of VT:79 is applied inside). */
+int as_mhsa_bwd(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt, const void* dot,
+                const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv, int B, int T, int Tpad,
+                int heads, as_stream_t stream);
+
 /* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] partial row sums in
  * column order (may be NULL).  rowsum_slices = 4: persistent schedule (needs ld = T rounded up to 128), one partial per
  * 32-column slice; rowsum_slices = 1: one CTA per tile, one partial per 128-column tile.

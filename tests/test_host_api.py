@@ -7,7 +7,8 @@ import torch.nn as nn
 
 def test_backbone_refuses_to_be_trained_silently():
     from attentionshift_b200.registry import build_backbone
-    cfg = dict(type='VisionTransformerDet', img_size=64, patch_size=16, embed_dim=128, depth=1, num_heads=2, mlp_ratio=4, qkv_bias=True)
+    cfg = dict(type='VisionTransformerDet', img_size=64, patch_size=16, embed_dim=128, depth=1, num_heads=2, mlp_ratio=4, qkv_bias=True,
+               train_backward=False)
     bb = build_backbone(dict(cfg))
     bb.train()
     with pytest.raises(RuntimeError, match='forward-only'):
