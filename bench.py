@@ -12,6 +12,7 @@ Workload = BASELINE.json configs[1]: bs8 1024x1024 ViT-B/16, 5 attention-shift i
 (weak scaling: every rank runs its own batch of 8; no data-path collective -- SURVEY.md 8e).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -50,6 +51,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
+    ap.add_argument('--mode', default='forward', choices=['forward', 'train'],
+                    help='forward (default, the BASELINE metric): backbone forward + seed_pseudo_gt; train: + backward of the backbone, '
+                         'DDP gradient all-reduce (NCCL) and the optimizer step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-config', action='store_true', help='skip the untouched-reference-config leg (cfg2, N=1)')
     ap.add_argument('--small', action='store_true', help='tiny config for a functional check (not a valid bench number)')
@@ -230,22 +234,44 @@ def count_launches(fn):
 def time_steps(fn, steps, barrier, per_step=None):
     """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream.  ``per_step``: list that
     receives the individual step times (an event after every step: no synchronisation, the timed region is unchanged)."""
-    barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    gc.collect()
+    gc.disable()            # like timeit: a generation-2 collection of the interpreter (tens of ms with a model's object graph alive)
+    barrier()               # inside a 25 ms step is the host's noise, not the path's -- it showed up as one 40-60 ms step in ten
     evs[0].record()
     for i in range(steps):
         fn()
         evs[i + 1].record()
     barrier()
+    gc.enable()
     if per_step is not None:
         per_step.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
     return evs[0].elapsed_time(evs[steps]) / steps
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE line, the JSON record.  Libraries write there too (NCCL prints its version / NCCL_DEBUG=INFO log
+    on fd 1): point fd 1 at stderr for the duration of the run -- the log stays visible for rank / transport checks -- and keep
+    the real stdout for ``emit``."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def run_ours(args):
     from attentionshift_b200 import parallel
-    if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
-        os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'   # NCCL's log stays visible (rank / transport checks) without touching stdout's JSON line
+    protect_stdout()
     rank, world, local = parallel.env_rank_world()
     # the host side of a rank is one launching thread: keep torch's CPU pool from oversubscribing the box when 8 ranks share it
     torch.set_num_threads(max(1, min(4, usable_cpus() // max(world, 1))))
@@ -311,12 +337,15 @@ def run_ours(args):
     for f in freed:
         f.record()
     e2e_loop(warm)                         # untimed: first use of the pinned mask buffers / copy stream (cudaHostAlloc is slow)
+    gc.collect()
+    gc.disable()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     d2h = e2e_loop(args.steps)
     e3.record()
     barrier()
+    gc.enable()
     ms_e2e = e2.elapsed_time(e3) / args.steps
     if sampler is not None:
         sampler.stop_flag = True
@@ -387,8 +416,9 @@ def run_ours(args):
                     'as_mean_shift_fused': 'round-1 persistent kernel + the token split kernel',
                     'as_mean_shift_tc': '~50 launches', 'as_mean_shift': 'fp32 CUDA-core kernels'}[ms_name]
             traffic2 = None
-            t2path = os.path.join(ROOT, 'profiles', 'ncu_msv2_traffic.json')      # dram bytes / launch from the committed ncu capture
-            if ms_name == 'as_mean_shift_v2' and os.path.exists(t2path) and not args.small and args.config == 'cfg2':
+            t2path = os.path.join(ROOT, 'profiles', {'as_mean_shift_v2': 'ncu_msv2_traffic.json',
+                                                     'as_mean_shift_fused': 'ncu_msfused_traffic.json'}.get(ms_name, 'none'))
+            if os.path.exists(t2path) and not args.small and args.config == 'cfg2':      # dram bytes / launch from the committed ncu capture
                 try:
                     traffic2 = json.load(open(t2path)).get('dram_bytes_per_launch')
                 except Exception:
@@ -414,7 +444,7 @@ def run_ours(args):
                     kernel_ms_per_step={k: round(v['ms'], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])})
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(cfg, steps=1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         parallel.barrier()
         torch.distributed.destroy_process_group()
@@ -499,9 +529,96 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------- training step
+def run_train(args):
+    """Training step of the hot path under DDP (reference: mmdet/apis/train.py:96-100 wraps the detector in
+    MMDistributedDataParallel, mmdet/utils/optimizer.py:23-38 scales the loss and steps the optimizer):
+        backbone forward with autograd (device kernels) -> seed_pseudo_gt without gradient (pseudo labels, DET:75-91)
+        -> surrogate loss on the backbone outputs the detector's losses consume (last_feat, point-token heads) -> backward on the
+        device kernels, gradient all-reduce overlapped by DDP's bucketing -> AdamW step.
+    The detector's own losses (RPN / RoI heads) are outside the hot path; the surrogate keeps every backbone parameter in the
+    graph so that the all-reduce moves the full 86 M-parameter gradient (344 MB in fp32)."""
+    from attentionshift_b200 import parallel
+    protect_stdout()
+    rank, world, local = parallel.env_rank_world()
+    torch.set_num_threads(max(1, min(4, usable_cpus() // max(world, 1))))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    parallel.init('nccl', dev)
+    cfg = dict(CONFIGS[args.config])
+    if args.small:
+        cfg.update(batch=2, img=(224, 224), depth=7)
+    cfg['cuda_graph'] = False
+    bb, head = build_models(cfg, dev)
+    bb.train()
+    model = bb
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(bb, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(bb.parameters(), lr=1e-5, weight_decay=0.05, fused=True)
+    inputs = make_inputs(cfg, rank)
+    img_dev = inputs[0].to(dev)
+    _, gt_points, pos_inds, gt_index, labels = inputs
+    hp, wp = cfg['img'][0] // 16, cfg['img'][1] // 16
+    n_params = sum(p.numel() for p in bb.parameters() if p.requires_grad)
+    loss_scale = 1024.0                                                 # static loss scale (apex O1 scales dynamically): fp16 GEMM operands in the backward
+
+    def step():
+        out = model(img_dev)
+        with torch.no_grad():
+            head.seed_pseudo_gt(None, None, None, None, None, vit_feat=out['last_feat'][:, 1:].detach().unflatten(1, (hp, wp)).permute(0, 3, 1, 2),
+                                point_cls=out['outputs_class'].detach(), point_reg=out['outputs_coord'].detach(), attns=out['attns'],
+                                gt_points=gt_points, gt_points_labels=labels, return_mask=False, pos_mask_thr=0.6, neg_mask_thr=0.1,
+                                num_mask_point_gt=10, corr_size=21, obj_tau=0.85, pos_inds=pos_inds, gt_index=gt_index)
+        loss = (out['last_feat'].float().pow(2).mean() + out['outputs_class'].float().pow(2).mean()
+                + out['outputs_coord'].float().pow(2).mean()) * loss_scale
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        parallel.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.rows = []
+    step_ms = []
+    ms = time_steps(step, args.steps, barrier, step_ms)
+    loss = float(step().detach()) / loss_scale
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    ms, = parallel.max_over_ranks([ms], device=dev)
+    if rank == 0:
+        B = cfg['batch']
+        line = dict(metric='images/sec, training step, ' + cfg['name'], value=round(world * B / (ms * 1e-3), 2), unit='images/s', n_gpus=world,
+                    steps=args.steps, warmup=warm, ms_per_step=round(ms, 3), step_ms=[round(v, 2) for v in step_ms], higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f16 operands / f32 accumulate (GEMMs, attention fwd + bwd), f32 (LayerNorm, GELU, AdamW, attention shift)',
+                    data='synthetic (random-init ViT weights, randn images, random GT points)',
+                    config=dict(workload=cfg['name'], per_gpu_batch=B,
+                                mode='train: backbone fwd + seed_pseudo_gt (no grad) + surrogate loss + backbone bwd + DDP gradient all-reduce (NCCL, '
+                                     '%d parameters = %.0f MB fp32 per step) + fused AdamW' % (n_params, n_params * 4 / 1e6),
+                                collective='torch DDP bucketed all-reduce overlapped with the backward' if world > 1 else 'none (1 rank)',
+                                loss=round(loss, 6)),
+                    clocks=sampler.summary() if sampler is not None else None)
+        emit(line)
+    if world > 1:
+        parallel.barrier()
+        torch.distributed.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.mode == 'train':
+        run_train(a)
     else:
         run_ours(a)

@@ -14,6 +14,8 @@ for W in "$@"; do
       python profiles/summarize_launches.py gpurun_out/launches_${TAG}.csv 40 > gpurun_out/launches_${TAG}_summary.txt; head -30 gpurun_out/launches_${TAG}_summary.txt;;
     ncu_ms)
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:mean_shift_v2 -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_msv2 python profiles/ncu_ms_target.py v2 > gpurun_out/ncu_${TAG}_msv2.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_msv2.log;;
+    ncu_msf)
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:mean_shift_fused -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_msfused python profiles/ncu_ms_target.py fused > gpurun_out/ncu_${TAG}_msfused.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_msfused.log;;
     ncu_hm)
       for V in headmean headmean_lean headmean_rows; do
         timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_headmean2 -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_$V python profiles/ncu_targets.py $V > gpurun_out/ncu_${TAG}_$V.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_$V.log
