@@ -455,9 +455,14 @@ def refined_maps_begin(cam_low, cam_mm, n_per_img, hp, wp, thr_pos=0.2, thr_neg=
     st.update(cam_low=cam_low, cam_mm=cam_mm, hp=hp, wp=wp)
     n_items = st['n_items']
 
+    d_kind, d_a, d_b = st['d_kind'], st['d_a'], st['d_b']
+
     def count(d_thr, levels=1):
+        # NB: closes over the tensors it needs, NOT over ``st`` -- ``st['count'] = count`` would otherwise make a reference cycle
+        # that keeps ~1 MB of device tensors per call alive until the cyclic GC runs; the caching allocator then keeps growing
+        # its pool and every growth is a cudaMalloc (seen as one 40-100 ms step in ten, profiles/step_outliers_r2.txt)
         rc = torch.empty(levels, n_items, H, device=dev, dtype=torch.int32)
-        _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(st['d_kind']), _p(st['d_a']), _p(st['d_b']), _p(d_thr), n_items,
+        _l.check(L.as_norm_rowcount(_p(cam_low), _p(cam_mm), _p(d_kind), _p(d_a), _p(d_b), _p(d_thr), n_items,
                                     hp, wp, levels, _p(rc), _sp()), 'as_norm_rowcount')
         return rc, d_thr, _Pending(rc.sum(2, dtype=torch.int32))
 

@@ -35,6 +35,7 @@ class LazyOutputs(dict):
         new = LazyOutputs({k: v for k, v in super().items() if k not in self._lazy_keys()})
         if self._arm is not None:
             self._arm(new)
+            new._arm = self._arm
         return new
 
     def _lazy_keys(self):
@@ -437,9 +438,9 @@ class VisionTransformerDet(nn.Module):
 
             d.set_lazy('org_feats', lambda: torch.stack(raw_features(), dim=1))
             d.set_lazy('feature', fpn_features)
-            d._arm = arm
 
         arm(ret)
+        ret._arm = arm          # (set from outside: a function that names itself is a reference cycle holding `features`)
         if self.with_point_head:
             ret['outputs_class'] = self.class_embed(point_tokens)
             ret['outputs_coord'] = self.bbox_embed(point_tokens).sigmoid()
