@@ -1,7 +1,8 @@
 """Multi-GPU plumbing for the hot path: one process per GPU, the image batch is the only sharded axis,
-there is NO data-path collective -- every stage from Attention.forward to pseudo_gt_masks is per image
+there is NO data-path collective in the forward -- every stage from Attention.forward to pseudo_gt_masks is per image
 (reference: batch is an outer python loop, RH:2267 / RH:2332; launch line run_train.py:9).
-torch.distributed is used for rendezvous, a barrier and the max-over-ranks reduction of the device timings only."""
+torch.distributed is used for rendezvous, a barrier, the max-over-ranks reduction of the device timings, and -- in training --
+the DDP gradient all-reduce (torch DDP, bench.py --mode train) and the packed reduction of the logging scalars below."""
 import os
 
 import torch
@@ -51,3 +52,30 @@ def sum_over_ranks(values, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.tolist()
+
+
+def parse_losses(losses):
+    """``BaseDetector._parse_losses`` (mmdet/models/detectors/base.py:185-216) with ONE collective and ONE host read.
+
+    The reference all-reduces every logged scalar separately and calls ``.item()`` after each (a host sync per loss key per
+    iteration -- SURVEY 8f rank 4: it caps multi-GPU scaling).  Same values here: per key the mean (a list of tensors sums its
+    means), ``loss`` = sum of the entries whose key contains 'loss'; then all log values travel in one packed tensor through a
+    single all-reduce (averaged over the ranks) and reach the host in a single copy.
+    -> (loss tensor with its autograd graph, OrderedDict of python floats in the reference's key order, 'loss' last)."""
+    from collections import OrderedDict
+    log_vars = OrderedDict()
+    for name, value in losses.items():
+        if isinstance(value, torch.Tensor):
+            log_vars[name] = value.mean()
+        elif isinstance(value, list):
+            log_vars[name] = sum(v.mean() for v in value)
+        else:
+            raise TypeError(f'{name} is not a tensor or list of tensors')
+    loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+    log_vars['loss'] = loss
+    packed = torch.stack([torch.as_tensor(v).detach().float().reshape(()) for v in log_vars.values()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        packed = packed / dist.get_world_size()
+        dist.all_reduce(packed)
+    host = packed.tolist()                                  # the one host read
+    return loss, OrderedDict((k, host[i]) for i, k in enumerate(log_vars))

@@ -21,8 +21,14 @@ WORKER = textwrap.dedent('''
     P.barrier()
     tmax = P.max_over_ranks([10.0 + rank, 5.0 - rank])
     tot = P.sum_over_ranks([local_sum, float(len(mine))])
+    # packed logging reduction (base.py:185-216 semantics with one all-reduce): rank r holds losses scaled by (r + 1)
+    w = torch.tensor(2.0, requires_grad=True)
+    losses = dict(loss_cls=w * (rank + 1) * torch.ones(3), loss_bbox=[w * 0.5 * (rank + 1), w * 0.25 * (rank + 1) * torch.ones(2)],
+                  acc=torch.tensor(10.0 * (rank + 1)))
+    loss, logs = P.parse_losses(losses)
+    loss.backward()
     if rank == 0:
-        print(json.dumps(dict(tmax=tmax, tot=tot, mine=mine)))
+        print(json.dumps(dict(tmax=tmax, tot=tot, mine=mine, logs=logs, local_loss=float(loss), grad=float(w.grad))))
     import torch.distributed as dist
     dist.destroy_process_group()
 ''')
@@ -51,6 +57,10 @@ def test_two_gloo_ranks_shard_and_reduce(tmp_path):
     assert res['tmax'] == [11.0, 5.0]                       # max over ranks of (10+rank, 5-rank)
     assert res['tot'] == [float(sum(i * i for i in range(13))), 13.0]   # the two shards partition the 13 images
     assert res['mine'] == list(range(7))
+    # mean over the two ranks of (r+1) x {2.0, 1.0 + 0.5, 10}: keys in the reference's order, 'loss' last, 'acc' not in the loss
+    assert list(res['logs']) == ['loss_cls', 'loss_bbox', 'acc', 'loss']
+    assert res['logs'] == dict(loss_cls=3.0, loss_bbox=2.25, acc=15.0, loss=5.25)
+    assert res['local_loss'] == 3.5 and res['grad'] == 1.75             # rank 0's own loss keeps its autograd graph
 
 
 def test_shards_partition_the_batch():
