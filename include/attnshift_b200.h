@@ -52,6 +52,11 @@ int as_mhsa_fwd(const void* q, const void* k, const void* vt, void* o, float* m,
    exponentials on the FMA pipe.  Env: AS_MHSA_VARIANT. */
 int as_mhsa_set_variant(int variant);
 
+/* VT:79-83 for the RoI decoders that reuse the ViT Block at T <= 197 with head_dim 32 (mae_bbox_head_rec.py:148-167,
+ * mae_mask_head_pointSup.py:172-190): qkv [B, T, 3, heads, head_dim] f16 = the qkv Linear's output as it lies, T <= 256,
+ * head_dim 32 or 64 -> o [B, T, heads*head_dim] f16.  One CTA per (head, batch item), K / V in shared memory, fp32 math. */
+int as_mhsa_small(const void* qkv, void* o, int B, int T, int heads, int head_dim, as_stream_t stream);
+
 /* Backward of as_mhsa_fwd (what torch autograd derives from VT:79-83 in the reference; needed for DDP training of the
  * backbone, mmdet/apis/train.py:96-100).  Flash style on tcgen05: P is recomputed from (q, k, m, l), nothing of size T x T is
  * stored; two deterministic kernels (dK / dV with a resident key tile, dQ with a resident query tile).
