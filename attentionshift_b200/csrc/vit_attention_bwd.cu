@@ -12,6 +12,9 @@
 // cores consume those tiles straight from shared memory -- as an MN-major A operand for the transposed products (P^T, dS^T),
 // K-major for dS K.  All B operands are K-major: the host passes Q^T, dO^T, K^T ([BH, 64, Tpad], like the forward's V^T) next
 // to the row-major tensors.
+// Pipelining: S / dP are produced per 64-key HALF (two N = 64 MMA groups with their own full / free barriers), so the tensor cores
+// compute the next half (or the next tile's first half) while the softmax warps work on the current one, and the transposed
+// products of tile i run in the shadow of tile i+1's first half.
 #include "common.cuh"
 
 using namespace asb;
@@ -21,7 +24,10 @@ namespace {
 constexpr int BT = 128, HD = 64;
 constexpr int TILE = BT * HD * 2;          // 16 KB: [128 rows x 64 halves], or a transposed tile as two [64 x 64] boxes
 constexpr int PTILE = BT * BT * 2;         // 32 KB: [128 q x 128 k] fp16 as two 64-column blocks of 16 KB
-constexpr int BWD_THREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2-5 softmax (TMEM lane quadrant = warp & 3)
+constexpr int BWD_THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2-17 softmax: TMEM lane quadrant = warp & 3, 32-column chunk =
+                                           // (warp - 2) >> 2.  One warp per scheduler was latency-bound (a dependent chain of ~1.5 k
+                                           // instructions per tile: 6 k cycles); four independent chunks per scheduler hide it.
+constexpr int SOFTMAX_WARPS = 16;
 constexpr uint32_t C_S = 0, C_DP = 128, C_ACC0 = 256, C_ACC1 = 320;
 
 struct BwdParams {
@@ -37,15 +43,15 @@ struct BwdParams {
 __device__ __forceinline__ int sw128p(int row, int col) {      // byte offset of (row, col) in a [rows x 64 halves] swizzled block
   return row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
 }
-__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// P and dS of one (query tile, key tile) pair from the S / dP accumulators of this thread's query row.
-// want_p: also write P (the dkv kernel needs both tiles, the dq kernel only dS).
+// P and dS for one 32-key CHUNK of a (query tile, key tile) pair from the S / dP accumulators of this thread's query row.
+// kWantP: also write P (the dkv kernel needs both tiles, the dq kernel only dS).
 template <bool kWantP>
-__device__ __forceinline__ void make_p_ds(uint32_t tm_row, uint8_t* p_s, uint8_t* ds_s, int row, bool row_ok, int k0, int T,
-                                          float c, float scale, float mi, float inv_l, float di) {
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
+__device__ __forceinline__ void make_p_ds_chunk(uint32_t tm_row, uint8_t* p_s, uint8_t* ds_s, int ch, int row, bool row_ok, int k0,
+                                                int T, float c, float scale, float mi, float inv_l, float di, uint64_t* p_free,
+                                                uint32_t p_free_parity) {
+  const int half = ch >> 1;
+  {
     uint32_t s[32], dp[32];
     tmem_ld_32x32(tm_row + C_S + ch * 32, s);
     tmem_ld_32x32(tm_row + C_DP + ch * 32, dp);
@@ -66,11 +72,12 @@ __device__ __forceinline__ void make_p_ds(uint32_t tm_row, uint8_t* p_s, uint8_t
       pw[i] = *reinterpret_cast<const uint32_t*>(&ph);
       dw[i] = *reinterpret_cast<const uint32_t*>(&dh);
     }
-    // 32 columns = 64 bytes = four 16-byte chunks of the row's 128-byte swizzled line in block (ch / 2)
-    const int blk = ch >> 1, cbase = (ch & 1) * 32;
+    mbar_wait(p_free, p_free_parity);                          // the previous tile's P / dS have been consumed by the tensor cores
+    // 32 columns = 64 bytes = four 16-byte chunks of the row's 128-byte swizzled line in block `half`
+    const int cbase = (ch & 1) * 32;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const int off = blk * (PTILE / 2) + sw128p(row, cbase + g * 8);
+      const int off = half * (PTILE / 2) + sw128p(row, cbase + g * 8);
       if (kWantP) *reinterpret_cast<uint4*>(p_s + off) = make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
       *reinterpret_cast<uint4*>(ds_s + off) = make_uint4(dw[4 * g], dw[4 * g + 1], dw[4 * g + 2], dw[4 * g + 3]);
     }
@@ -96,12 +103,12 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* kv_full = bars;                  // 1
   uint64_t* full = bars + 1;                 // 2
   uint64_t* empty = bars + 3;                // 2
-  uint64_t* s_full = bars + 5;               // S, dP ready (commit)
-  uint64_t* s_free = bars + 6;               // S, dP read (4 warps)
-  uint64_t* p_full = bars + 7;               // P, dS written (4 warps)
-  uint64_t* p_free = bars + 8;               // P, dS consumed (commit)
-  uint64_t* acc_full = bars + 9;             // all MMAs done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 5;               // 2: S, dP of a 64-key half ready (commit)
+  uint64_t* s_free = bars + 7;               // 2: that half read (4 warps)
+  uint64_t* p_full = bars + 9;               // P, dS written (4 warps)
+  uint64_t* p_free = bars + 10;              // P, dS consumed (commit)
+  uint64_t* acc_full = bars + 11;            // all MMAs done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, bh = blockIdx.z * p.heads + blockIdx.y;
   const int k0 = jt * BT;
@@ -110,8 +117,8 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_dot);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(p_free, 1); mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], SOFTMAX_WARPS / 2); }
+    mbar_init(p_full, SOFTMAX_WARPS); mbar_init(p_free, 1); mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -139,27 +146,40 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = umma_idesc(0, BT, BT);                       // S, dP: M = 128 q, N = 128 k
+    constexpr uint32_t idesc_h = umma_idesc(0, BT, 64);                       // S, dP of one half: M = 128 q, N = 64 k
     constexpr uint32_t idesc_t = umma_idesc(0, BT, HD) | (1u << 15);          // dV, dK: M = 128 k (A MN-major), N = 64 d
     mbar_wait(kv_full, 0);
-    for (int it = 0; it < p.nt; ++it) {
-      const int st = it & 1;
-      mbar_wait(&full[st], (it >> 1) & 1);
-      mbar_wait(s_free, (it & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t q_a = smem_u32(ring + st * DKV_STAGE), do_a = q_a + TILE, qt_a = q_a + 2 * TILE, dot_a = q_a + 3 * TILE;
+    // S / dP of (tile, half): Q_i K_j[half]^T and dO_i V_j[half]^T into their 64-column slots
+    auto issue_half = [&](int it, int half) {
+      const uint32_t q_a = smem_u32(ring + (it & 1) * DKV_STAGE), do_a = q_a + TILE;
+      const uint32_t kh = smem_u32(k_s) + half * (TILE / 2), vh = smem_u32(v_s) + half * (TILE / 2);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          mma_f16_ss(tmem + C_S, umma_desc_k_sw128(q_a + k * 32), umma_desc_k_sw128(smem_u32(k_s) + k * 32), idesc_s, k != 0);
+          mma_f16_ss(tmem + C_S + half * 64, umma_desc_k_sw128(q_a + k * 32), umma_desc_k_sw128(kh + k * 32), idesc_h, k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          mma_f16_ss(tmem + C_DP, umma_desc_k_sw128(do_a + k * 32), umma_desc_k_sw128(smem_u32(v_s) + k * 32), idesc_s, k != 0);
-        tc_commit(s_full);
+          mma_f16_ss(tmem + C_DP + half * 64, umma_desc_k_sw128(do_a + k * 32), umma_desc_k_sw128(vh + k * 32), idesc_h, k != 0);
+        tc_commit(&s_full[half]);
       }
       __syncwarp();
+    };
+    mbar_wait(&full[0], 0);
+    tc_fence_after();
+    issue_half(0, 0);
+    issue_half(0, 1);
+    for (int it = 0; it < p.nt; ++it) {
+      const int st = it & 1;
+      const bool more = it + 1 < p.nt;
+      if (more) {                                              // first half of the next tile as soon as this tile's first half is read
+        mbar_wait(&full[st ^ 1], ((it + 1) >> 1) & 1);
+        mbar_wait(&s_free[0], it & 1);
+        tc_fence_after();
+        issue_half(it + 1, 0);
+      }
       mbar_wait(p_full, it & 1);
       tc_fence_after();
+      const uint32_t q_a = smem_u32(ring + st * DKV_STAGE), qt_a = q_a + 2 * TILE, dot_a = q_a + 3 * TILE;
       if (elect_one()) {
         const uint32_t pa = smem_u32(p_s), da = smem_u32(ds_s);
 #pragma unroll
@@ -168,47 +188,48 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mma_f16_ss(tmem + C_ACC1, umma_desc_mn_sw128(pa + k * 2048, PTILE / 2), umma_desc_k_sw128(dot_a + boff), idesc_t, (it | k) != 0);
           mma_f16_ss(tmem + C_ACC0, umma_desc_mn_sw128(da + k * 2048, PTILE / 2), umma_desc_k_sw128(qt_a + boff), idesc_t, (it | k) != 0);
         }
-        tc_commit(&empty[st]);
         tc_commit(p_free);
-        if (it == p.nt - 1) tc_commit(acc_full);
+        if (!more) { tc_commit(&empty[st]); tc_commit(acc_full); }
       }
       __syncwarp();
+      if (more) {                                              // second half of the next tile (p_full implies s_free[1] of this tile)
+        mbar_wait(&s_free[1], it & 1);
+        tc_fence_after();
+        issue_half(it + 1, 1);
+        if (elect_one()) tc_commit(&empty[st]);                // everything that read stage `st` has been issued before this commit
+        __syncwarp();
+      }
     }
   } else {
-    const int quad = warp & 3, row = quad * 32 + lane;
+    const int quad = warp & 3, row = quad * 32 + lane, ch = (warp - 2) >> 2, half = ch >> 1;
     const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
     for (int it = 0; it < p.nt; ++it) {
       const int t = it * BT + row;
       const bool ok = t < p.T;
       const size_t si = (size_t)bh * p.T + (ok ? t : 0);
       const float mi = p.m[si], inv_l = 1.f / p.l[si], di = p.delta[si];
-      mbar_wait(s_full, it & 1);
+      mbar_wait(&s_full[half], it & 1);
       tc_fence_after();
-      mbar_wait(p_free, (it & 1) ^ 1);                          // the previous tile's P / dS have been consumed
-      make_p_ds<true>(tm_row, p_s, ds_s, row, ok, k0, p.T, p.scale_log2, p.scale, mi, inv_l, di);
+      make_p_ds_chunk<true>(tm_row, p_s, ds_s, ch, row, ok, k0, p.T, p.scale_log2, p.scale, mi, inv_l, di, p_free, (it & 1) ^ 1);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+      if (lane == 0) { mbar_arrive(&s_free[half]); mbar_arrive(p_full); }
     }
-    // epilogue: thread = key row
+    // epilogue: thread = key row; the four chunk groups take dK[:, 0:32], dK[:, 32:64], dV[:, 0:32], dV[:, 32:64]
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int kr = k0 + row;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      uint32_t a[32], b[32];
-      tmem_ld_32x32(tm_row + C_ACC0 + half * 32, a);
-      tmem_ld_32x32(tm_row + C_ACC1 + half * 32, b);
+    {
+      const int hf = ch & 1;
+      uint32_t a[32];
+      tmem_ld_32x32(tm_row + (ch < 2 ? C_ACC0 : C_ACC1) + hf * 32, a);
       tc_wait_ld();
       if (kr < p.T) {
-        float4* dk = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + kr) * HD + half * 32);
-        float4* dv = reinterpret_cast<float4*>(p.out1 + ((size_t)bh * p.T + kr) * HD + half * 32);
+        float4* dst = reinterpret_cast<float4*>((ch < 2 ? p.out0 : p.out1) + ((size_t)bh * p.T + kr) * HD + hf * 32);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          dk[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
-          dv[g] = make_float4(__uint_as_float(b[4 * g]), __uint_as_float(b[4 * g + 1]), __uint_as_float(b[4 * g + 2]), __uint_as_float(b[4 * g + 3]));
-        }
+        for (int g = 0; g < 8; ++g)
+          dst[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
       }
     }
     tc_fence_before();
@@ -236,12 +257,12 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* q_full = bars;
   uint64_t* full = bars + 1;
   uint64_t* empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_free = bars + 8;
-  uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 5;               // 2
+  uint64_t* s_free = bars + 7;               // 2
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_free = bars + 10;
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, bh = blockIdx.z * p.heads + blockIdx.y;
   const int q0 = qt * BT;
@@ -249,8 +270,8 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_kt);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(p_free, 1); mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], SOFTMAX_WARPS / 2); }
+    mbar_init(p_full, SOFTMAX_WARPS); mbar_init(p_free, 1); mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -276,27 +297,38 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = umma_idesc(0, BT, BT);
+    constexpr uint32_t idesc_h = umma_idesc(0, BT, 64);                       // S, dP of one half: M = 128 q, N = 64 k
     constexpr uint32_t idesc_q = umma_idesc(0, BT, HD);                       // dQ: M = 128 q, N = 64 d, both K-major
     mbar_wait(q_full, 0);
-    for (int it = 0; it < p.nt; ++it) {
-      const int st = it & 1;
-      mbar_wait(&full[st], (it >> 1) & 1);
-      mbar_wait(s_free, (it & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t k_a = smem_u32(ring + st * DQ_STAGE), v_a = k_a + TILE, kt_a = k_a + 2 * TILE;
+    auto issue_half = [&](int it, int half) {
+      const uint32_t k_a = smem_u32(ring + (it & 1) * DQ_STAGE) + half * (TILE / 2), v_a = k_a + TILE;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          mma_f16_ss(tmem + C_S, umma_desc_k_sw128(smem_u32(q_s) + k * 32), umma_desc_k_sw128(k_a + k * 32), idesc_s, k != 0);
+          mma_f16_ss(tmem + C_S + half * 64, umma_desc_k_sw128(smem_u32(q_s) + k * 32), umma_desc_k_sw128(k_a + k * 32), idesc_h, k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          mma_f16_ss(tmem + C_DP, umma_desc_k_sw128(smem_u32(do_s) + k * 32), umma_desc_k_sw128(v_a + k * 32), idesc_s, k != 0);
-        tc_commit(s_full);
+          mma_f16_ss(tmem + C_DP + half * 64, umma_desc_k_sw128(smem_u32(do_s) + k * 32), umma_desc_k_sw128(v_a + k * 32), idesc_h, k != 0);
+        tc_commit(&s_full[half]);
       }
       __syncwarp();
+    };
+    mbar_wait(&full[0], 0);
+    tc_fence_after();
+    issue_half(0, 0);
+    issue_half(0, 1);
+    for (int it = 0; it < p.nt; ++it) {
+      const int st = it & 1;
+      const bool more = it + 1 < p.nt;
+      if (more) {
+        mbar_wait(&full[st ^ 1], ((it + 1) >> 1) & 1);
+        mbar_wait(&s_free[0], it & 1);
+        tc_fence_after();
+        issue_half(it + 1, 0);
+      }
       mbar_wait(p_full, it & 1);
       tc_fence_after();
+      const uint32_t kt_a = smem_u32(ring + st * DQ_STAGE) + 2 * TILE;
       if (elect_one()) {
         const uint32_t da = smem_u32(ds_s);
 #pragma unroll
@@ -305,38 +337,42 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t boff = (k >> 2) * (TILE / 2) + (k & 3) * 32;
           mma_f16_ss(tmem + C_ACC0, umma_desc_k_sw128(da + aoff), umma_desc_k_sw128(kt_a + boff), idesc_q, (it | k) != 0);
         }
-        tc_commit(&empty[st]);
         tc_commit(p_free);
-        if (it == p.nt - 1) tc_commit(acc_full);
+        if (!more) { tc_commit(&empty[st]); tc_commit(acc_full); }
       }
       __syncwarp();
+      if (more) {
+        mbar_wait(&s_free[1], it & 1);
+        tc_fence_after();
+        issue_half(it + 1, 1);
+        if (elect_one()) tc_commit(&empty[st]);
+        __syncwarp();
+      }
     }
   } else {
-    const int quad = warp & 3, row = quad * 32 + lane;
+    const int quad = warp & 3, row = quad * 32 + lane, ch = (warp - 2) >> 2, half = ch >> 1;
     const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
     const int t = q0 + row;
     const bool ok = t < p.T;
     const size_t si = (size_t)bh * p.T + (ok ? t : 0);
     const float mi = p.m[si], inv_l = 1.f / p.l[si], di = p.delta[si];
     for (int it = 0; it < p.nt; ++it) {
-      mbar_wait(s_full, it & 1);
+      mbar_wait(&s_full[half], it & 1);
       tc_fence_after();
-      mbar_wait(p_free, (it & 1) ^ 1);
-      make_p_ds<false>(tm_row, nullptr, ds_s, row, ok, it * BT, p.T, p.scale_log2, p.scale, mi, inv_l, di);
+      make_p_ds_chunk<false>(tm_row, nullptr, ds_s, ch, row, ok, it * BT, p.T, p.scale_log2, p.scale, mi, inv_l, di, p_free, (it & 1) ^ 1);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+      if (lane == 0) { mbar_arrive(&s_free[half]); mbar_arrive(p_full); }
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    if (ch < 2) {                                               // thread = query row; chunk groups 0 / 1 take dQ[:, 0:32] / dQ[:, 32:64]
       uint32_t a[32];
-      tmem_ld_32x32(tm_row + C_ACC0 + half * 32, a);
+      tmem_ld_32x32(tm_row + C_ACC0 + ch * 32, a);
       tc_wait_ld();
       if (ok) {
-        float4* dq = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + t) * HD + half * 32);
+        float4* dq = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + t) * HD + ch * 32);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           dq[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));

@@ -122,3 +122,46 @@ extern "C" int as_assemble_tokens(const float* emb, const float* cls, const floa
   AS_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------ batched transpose with zero padding (training path)
+// src [batch, R, C] f16 (rows contiguous) -> dst [batch, C, Rp] f16, dst[b, c, r] = src[b, r, c] for r < R and 0 for R <= r < Rp.
+// The backward GEMMs and the attention backward take K-major operands: dW = dY^T X needs dY^T and X^T with the token dimension
+// contiguous (and padded to the GEMM's K granule), the attention backward needs Q^T, K^T, dO^T ([64, Tpad] per head).  A
+// strided torch copy does this at ~0.3 TB/s; 64 x 64 tiles through shared memory keep both sides coalesced.
+namespace {
+__global__ void __launch_bounds__(256) transpose_pad_f16_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int R, int C,
+                                                               int Rp) {
+  __shared__ __half tile[64][66];
+  const int b = blockIdx.z, r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const __half* s = src + (size_t)b * R * C;
+  __half* d = dst + (size_t)b * C * Rp;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    __half2 v = __floats2half2_rn(0.f, 0.f);
+    if (r < R) {
+      if (c + 1 < C) v = *reinterpret_cast<const __half2*>(s + (size_t)r * C + c);
+      else if (c < C) v = __halves2half2(s[(size_t)r * C + c], __float2half(0.f));
+    }
+    tile[i][2 * tx] = __low2half(v);
+    tile[i][2 * tx + 1] = __high2half(v);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c < C && r < Rp) {
+      const __half2 v = __halves2half2(tile[2 * tx][i], tile[2 * tx + 1][i]);
+      if (r + 1 < Rp) *reinterpret_cast<__half2*>(d + (size_t)c * Rp + r) = v;
+      else d[(size_t)c * Rp + r] = __low2half(v);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int as_transpose_pad_f16(const void* src, void* dst, int batch, int R, int C, int Rp, cudaStream_t stream) {
+  if (batch < 1 || R < 1 || C < 1 || Rp < R || (C & 1) || (Rp & 1)) return AS_ERR_BAD_ARG;
+  const dim3 grid((Rp + 63) / 64, (C + 63) / 64, batch);
+  transpose_pad_f16_kernel<<<grid, 256, 0, stream>>>((const __half*)src, (__half*)dst, R, C, Rp);
+  AS_LAUNCH_CHECK();
+  return 0;
+}

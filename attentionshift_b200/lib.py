@@ -24,6 +24,7 @@ SIGNATURES = {
     'as_assemble_tokens': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_bwd': (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp]),
+    'as_transpose_pad_f16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_small': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_set_variant': (_i, [_i]),
     'as_mt19937_draws': (_i, [_vp, _i, _i, _vp]),

@@ -21,11 +21,20 @@ from . import lib as _l
 from . import ops
 
 
-def _pad_t(x, Tpad):
-    """[..., T, 64] -> transposed, zero padded [..., 64, Tpad] (the K-major B operand layout of the backward kernels)."""
-    out = x.new_zeros(*x.shape[:-2], x.shape[-1], Tpad)
-    out[..., :x.shape[-2]] = x.transpose(-1, -2)
+def transpose_pad(x, Rp):
+    """[batch..., R, C] fp16 -> [batch..., C, Rp] fp16, zero padded for rows >= R (``as_transpose_pad_f16``: the K-major operand
+    layout of the backward GEMMs and of the attention backward)."""
+    L = _l.load()
+    x = x.contiguous()
+    R, C = x.shape[-2], x.shape[-1]
+    batch = x.numel() // (R * C)
+    out = torch.empty(*x.shape[:-2], C, Rp, device=x.device, dtype=torch.float16)
+    _l.check(L.as_transpose_pad_f16(_l.ptr(x), _l.ptr(out), batch, R, C, Rp, _l.stream_ptr()), 'as_transpose_pad_f16')
     return out
+
+
+def _pad_t(x, Tpad):
+    return transpose_pad(x, Tpad)
 
 
 def mhsa_bwd(q, k, vt, o, d_o, m, l, T):
@@ -36,7 +45,7 @@ def mhsa_bwd(q, k, vt, o, d_o, m, l, T):
     Tpad = vt.shape[-1]
     d_oh = d_o.reshape(B, T, h, 64).permute(0, 2, 1, 3).contiguous().half()                   # [B,h,T,64]
     delta = (d_o.float() * o.float()).reshape(B, T, h, 64).sum(-1).permute(0, 2, 1).contiguous()   # [B,h,T]
-    v = vt[..., :T].transpose(-1, -2).contiguous()
+    v = transpose_pad(vt, 64)[..., :T, :].contiguous()                                       # [B,h,T,64]
     qt, kt, dot = _pad_t(q, Tpad), _pad_t(k, Tpad), _pad_t(d_oh, Tpad)
     dq = torch.empty(B, h, T, 64, device=q.device, dtype=torch.float32)
     dk, dv = torch.empty_like(dq), torch.empty_like(dq)
@@ -54,11 +63,7 @@ def _linear_grads(x16, weight, dy16, need_dx, need_dw):
         dx = ops.linear_f16(dy16, weight.detach().t().contiguous().half(), None, ops.EPI_F16)        # [M,K]
     if need_dw:
         Mp = (M + 63) // 64 * 64
-        dyt = dy16.new_zeros(N, Mp)
-        dyt[:, :M] = dy16.t()
-        xt = x16.new_zeros(K, Mp)
-        xt[:, :M] = x16.t()
-        dw = ops.linear_f16(dyt, xt, None, ops.EPI_F32)                                              # [N,K] fp32
+        dw = ops.linear_f16(transpose_pad(dy16, Mp), transpose_pad(x16, Mp), None, ops.EPI_F32)      # [N,K] fp32
     return dx, dw
 
 
@@ -80,6 +85,26 @@ class LinearFn(torch.autograd.Function):
         dx, dw = _linear_grads(x16, weight, dy16, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         db = dy.float().sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None
+
+
+class LinearResidFn(torch.autograd.Function):
+    """y = resid + x16 @ weight^T + bias in one kernel (the GEMM's fp32 residual epilogue): VT:114-115's ``x + f(x)``."""
+
+    @staticmethod
+    def forward(ctx, x16, weight, bias, resid):
+        y = ops.linear_f16(x16, weight.detach().half().contiguous(), None if bias is None else bias.detach().float(),
+                           ops.EPI_RESID_F32, resid=resid.contiguous())
+        ctx.save_for_backward(x16, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, weight = ctx.saved_tensors
+        dy16 = dy.half().contiguous()
+        dx, dw = _linear_grads(x16, weight, dy16, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        db = dy.float().sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, dy
 
 
 class AttentionFn(torch.autograd.Function):
@@ -120,8 +145,8 @@ def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None):
     if want_attn:
         with torch.no_grad():
             attn, _ = ops.attn_headmean(q, k, m, l, T, **(headmean_kwargs or {}))
-    x = x + LinearFn.apply(o, blk.attn.proj.weight, blk.attn.proj.bias, True)
+    x = LinearResidFn.apply(o, blk.attn.proj.weight, blk.attn.proj.bias, x)
     xn = F.layer_norm(x, (C,), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps).half()
-    hid = F.gelu(LinearFn.apply(xn, blk.mlp.fc1.weight, blk.mlp.fc1.bias, True)).half()
-    x = x + LinearFn.apply(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, True)
+    hid = F.gelu(LinearFn.apply(xn, blk.mlp.fc1.weight, blk.mlp.fc1.bias, False))       # fp16 in / out, fp32 inside
+    x = LinearResidFn.apply(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, x)
     return x, attn

@@ -57,6 +57,11 @@ int as_mhsa_set_variant(int variant);
  * head_dim 32 or 64 -> o [B, T, heads*head_dim] f16.  One CTA per (head, batch item), K / V in shared memory, fp32 math. */
 int as_mhsa_small(const void* qkv, void* o, int B, int T, int heads, int head_dim, as_stream_t stream);
 
+/* Training path: batched transpose with zero padding, src [batch, R, C] f16 -> dst [batch, C, Rp] f16 (Rp >= R, C and Rp even).
+ * Makes the K-major operands of the backward GEMMs (dW = dY^T X) and of as_mhsa_bwd (Q^T, K^T, dO^T) -- torch autograd's own
+ * backward of VT:76-84 transposes implicitly inside cuBLAS. */
+int as_transpose_pad_f16(const void* src, void* dst, int batch, int R, int C, int Rp, as_stream_t stream);
+
 /* Backward of as_mhsa_fwd (what torch autograd derives from VT:79-83 in the reference; needed for DDP training of the
  * backbone, mmdet/apis/train.py:96-100).  Flash style on tcgen05: P is recomputed from (q, k, m, l), nothing of size T x T is
  * stored; two deterministic kernels (dK / dV with a resident key tile, dQ with a resident query tile).

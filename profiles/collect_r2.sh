@@ -20,6 +20,10 @@ for W in "$@"; do
       for V in headmean headmean_lean headmean_rows; do
         timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_headmean2 -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_$V python profiles/ncu_targets.py $V > gpurun_out/ncu_${TAG}_$V.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_$V.log
       done;;
+    ncu_bwd)
+      for K in mhsa_bwd_dkv mhsa_bwd_dq; do
+        timeout 300 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_$K python profiles/ncu_targets.py mhsa_bwd > gpurun_out/ncu_${TAG}_$K.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_$K.log
+      done;;
     ncu_mhsa)
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:mhsa_fwd2 -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_mhsa python profiles/ncu_targets.py mhsa > gpurun_out/ncu_${TAG}_mhsa.log 2>&1; tail -1 gpurun_out/ncu_${TAG}_mhsa.log;;
   esac

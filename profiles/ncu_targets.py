@@ -31,3 +31,11 @@ for _ in range(2):
         elif which == 'headmean_rows':     # the last layer: point-token rows only
             ops.attn_headmean(q, k, m, l, T, want_transposed=False, row0=T - 100)
 torch.cuda.synchronize()
+if which == 'mhsa_bwd':        # attention backward at the cfg2 shapes (training path)
+    from attentionshift_b200 import training
+    q, k, vt = ops.qkv_proj(x768, w_qkv, b2304, B, T, H, Tpad)
+    o, m, l = ops.mhsa_fwd(q, k, vt, T)
+    g = torch.randn(B, T, C, device=dev)
+    for _ in range(2):
+        training.mhsa_bwd(q, k, vt, o, g, m, l, T)
+    torch.cuda.synchronize()
