@@ -57,20 +57,33 @@ __device__ __forceinline__ void make_p_ds_chunk(uint32_t tm_row, uint8_t* p_s, u
     tmem_ld_32x32(tm_row + C_DP + ch * 32, dp);
     tc_wait_ld();
     uint32_t pw[16], dw[16];
+    const bool full_tile = k0 + ch * 32 + 32 <= T;               // every column of the chunk is a real key (all tiles but the last)
+    if (row_ok && full_tile) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float pv[2], dv[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = ch * 32 + 2 * i + e;
-        const bool ok = row_ok && (k0 + col < T);
-        const float p = ok ? ex2_approx(fmaf(__uint_as_float(s[2 * i + e]), c, -mi)) * inv_l : 0.f;
-        pv[e] = p;
-        dv[e] = p * (__uint_as_float(dp[2 * i + e]) - di) * scale;
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c, -mi)) * inv_l;
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c, -mi)) * inv_l;
+        const float d0 = p0 * (__uint_as_float(dp[2 * i]) - di) * scale, d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - di) * scale;
+        const __half2 ph = __floats2half2_rn(p0, p1), dh = __floats2half2_rn(d0, d1);
+        pw[i] = *reinterpret_cast<const uint32_t*>(&ph);
+        dw[i] = *reinterpret_cast<const uint32_t*>(&dh);
       }
-      const __half2 ph = __floats2half2_rn(pv[0], pv[1]), dh = __floats2half2_rn(dv[0], dv[1]);
-      pw[i] = *reinterpret_cast<const uint32_t*>(&ph);
-      dw[i] = *reinterpret_cast<const uint32_t*>(&dh);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = ch * 32 + 2 * i + e;
+          const bool ok = row_ok && (k0 + col < T);
+          const float p = ok ? ex2_approx(fmaf(__uint_as_float(s[2 * i + e]), c, -mi)) * inv_l : 0.f;
+          pv[e] = p;
+          dv[e] = p * (__uint_as_float(dp[2 * i + e]) - di) * scale;
+        }
+        const __half2 ph = __floats2half2_rn(pv[0], pv[1]), dh = __floats2half2_rn(dv[0], dv[1]);
+        pw[i] = *reinterpret_cast<const uint32_t*>(&ph);
+        dw[i] = *reinterpret_cast<const uint32_t*>(&dh);
+      }
     }
     mbar_wait(p_free, p_free_parity);                          // the previous tile's P / dS have been consumed by the tensor cores
     // 32 columns = 64 bytes = four 16-byte chunks of the row's 128-byte swizzled line in block `half`
@@ -177,6 +190,11 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_after();
         issue_half(it + 1, 0);
       }
+      if (more) {                                              // second half of the next tile BEFORE this tile's transposed products:
+        mbar_wait(&s_free[1], it & 1);                         // its softmax warps start 512 tensor cycles earlier, and dV / dK run
+        tc_fence_after();                                      // in the shadow of their exponentials
+        issue_half(it + 1, 1);
+      }
       mbar_wait(p_full, it & 1);
       tc_fence_after();
       const uint32_t q_a = smem_u32(ring + st * DKV_STAGE), qt_a = q_a + 2 * TILE, dot_a = q_a + 3 * TILE;
@@ -189,25 +207,21 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mma_f16_ss(tmem + C_ACC0, umma_desc_mn_sw128(da + k * 2048, PTILE / 2), umma_desc_k_sw128(qt_a + boff), idesc_t, (it | k) != 0);
         }
         tc_commit(p_free);
-        if (!more) { tc_commit(&empty[st]); tc_commit(acc_full); }
+        tc_commit(&empty[st]);                                 // everything that read stage `st` has been issued before this commit
+        if (!more) tc_commit(acc_full);
       }
       __syncwarp();
-      if (more) {                                              // second half of the next tile (p_full implies s_free[1] of this tile)
-        mbar_wait(&s_free[1], it & 1);
-        tc_fence_after();
-        issue_half(it + 1, 1);
-        if (elect_one()) tc_commit(&empty[st]);                // everything that read stage `st` has been issued before this commit
-        __syncwarp();
-      }
     }
   } else {
     const int quad = warp & 3, row = quad * 32 + lane, ch = (warp - 2) >> 2, half = ch >> 1;
     const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+    float n_m = 0.f, n_l = 1.f, n_d = 0.f;                       // the next tile's row statistics, loaded one tile ahead
+    if (row < p.T) { const size_t s0 = (size_t)bh * p.T + row; n_m = p.m[s0]; n_l = p.l[s0]; n_d = p.delta[s0]; }
     for (int it = 0; it < p.nt; ++it) {
       const int t = it * BT + row;
       const bool ok = t < p.T;
-      const size_t si = (size_t)bh * p.T + (ok ? t : 0);
-      const float mi = p.m[si], inv_l = 1.f / p.l[si], di = p.delta[si];
+      const float mi = n_m, inv_l = 1.f / n_l, di = n_d;
+      if (t + BT < p.T) { const size_t s1 = (size_t)bh * p.T + t + BT; n_m = p.m[s1]; n_l = p.l[s1]; n_d = p.delta[s1]; }
       mbar_wait(&s_full[half], it & 1);
       tc_fence_after();
       make_p_ds_chunk<true>(tm_row, p_s, ds_s, ch, row, ok, k0, p.T, p.scale_log2, p.scale, mi, inv_l, di, p_free, (it & 1) ^ 1);
@@ -326,6 +340,11 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_after();
         issue_half(it + 1, 0);
       }
+      if (more) {
+        mbar_wait(&s_free[1], it & 1);
+        tc_fence_after();
+        issue_half(it + 1, 1);
+      }
       mbar_wait(p_full, it & 1);
       tc_fence_after();
       const uint32_t kt_a = smem_u32(ring + st * DQ_STAGE) + 2 * TILE;
@@ -338,16 +357,10 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           mma_f16_ss(tmem + C_ACC0, umma_desc_k_sw128(da + aoff), umma_desc_k_sw128(kt_a + boff), idesc_q, (it | k) != 0);
         }
         tc_commit(p_free);
-        if (!more) { tc_commit(&empty[st]); tc_commit(acc_full); }
+        tc_commit(&empty[st]);
+        if (!more) tc_commit(acc_full);
       }
       __syncwarp();
-      if (more) {
-        mbar_wait(&s_free[1], it & 1);
-        tc_fence_after();
-        issue_half(it + 1, 1);
-        if (elect_one()) tc_commit(&empty[st]);
-        __syncwarp();
-      }
     }
   } else {
     const int quad = warp & 3, row = quad * 32 + lane, ch = (warp - 2) >> 2, half = ch >> 1;
