@@ -583,7 +583,7 @@ def run_train(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, 6)          # the caching allocator needs a few full fwd + bwd steps to stop growing (each growth is a cudaMalloc)
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
