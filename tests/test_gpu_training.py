@@ -71,3 +71,15 @@ def test_backbone_parameter_gradients_vs_oracle(embed, heads, depth, img, n_pt):
     bad = {k: v for k, v in worst.items() if v > 2e-2}
     print('parameter gradients, worst max-norm relative errors:', sorted(worst.items(), key=lambda kv: -kv[1])[:6])
     assert len(worst) >= 4 + 12 * depth and not bad, bad
+
+
+@pytest.mark.parametrize('batch,R,C,Rp', [(1, 100, 64, 128), (3, 4197, 64, 4224), (1, 33576, 768, 33600), (2, 65, 130, 66)])
+def test_transpose_pad(batch, R, C, Rp):
+    """as_transpose_pad_f16: [batch, R, C] -> [batch, C, Rp], zero padded rows (the K-major operands of the backward GEMMs and of
+    as_mhsa_bwd) -- bit-exact against torch."""
+    from attentionshift_b200 import training
+    x = torch.randn(batch, R, C, device='cuda').half()
+    y = training.transpose_pad(x, Rp)
+    ref = torch.zeros(batch, C, Rp, device='cuda', dtype=torch.float16)
+    ref[..., :R] = x.transpose(-1, -2)
+    assert torch.equal(y, ref)
