@@ -214,3 +214,56 @@ extern "C" int as_part_centers(const float* pmap, const int* n_parts, const floa
   AS_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------ RoIAlign for the MIL layer selection
+// RH:2953-2972 pools every per-layer pseudo box with mmcv's RoIAlign (configs/mae/attnshift_voc12aug.py:64-68: output 7 x 7,
+// sampling_ratio 0 = adaptive, stride 16, aligned=True) before MAEBoxHeadMIL scores it.  Same arithmetic as the published
+// RoIAlign (aligned: box * scale - 0.5; per bin ceil(roi / 7) x ceil(roi / 7) bilinear samples, average), on the TOKEN-MAJOR
+// feature map [n_img, hp*wp, C] (no [B,C,Hp,Wp] transpose), writing [n_roi, 49, C] fp32 -- the row layout the head's LayerNorm /
+// decoder_embed GEMM consume (MIL:146-150 flattens to exactly this).  One CTA per (bin, roi), threads over channels.
+namespace {
+__global__ void __launch_bounds__(128) roi_align_tokens_kernel(const float* __restrict__ feats, long long fstride, const float* __restrict__ rois,
+                                                               int hp, int wp, int C, int pooled, float scale, float* __restrict__ out) {
+  const int bin = blockIdx.x, r = blockIdx.y;
+  const int ph = bin / pooled, pw = bin - ph * pooled;
+  const float* roi = rois + 5 * r;
+  const int img = (int)roi[0];
+  const float x0 = roi[1] * scale - 0.5f, y0 = roi[2] * scale - 0.5f, x1 = roi[3] * scale - 0.5f, y1 = roi[4] * scale - 0.5f;
+  const float rw = x1 - x0, rh = y1 - y0;
+  const float bw = rw / (float)pooled, bh = rh / (float)pooled;
+  const int gh = max((int)ceilf(rh / (float)pooled), 1) , gw = max((int)ceilf(rw / (float)pooled), 1);
+  const float cnt = (float)max(gh * gw, 1);
+  const float* f = feats + img * fstride;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      float y = y0 + ph * bh + (iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        float x = x0 + pw * bw + (ix + 0.5f) * bw / (float)gw;
+        float yy = y;
+        if (yy < -1.f || yy > (float)hp || x < -1.f || x > (float)wp) continue;      // outside the map: contributes 0
+        yy = fmaxf(yy, 0.f);
+        x = fmaxf(x, 0.f);
+        int yl = (int)yy, xl = (int)x, yh, xh;
+        if (yl >= hp - 1) { yh = yl = hp - 1; yy = (float)yl; } else yh = yl + 1;
+        if (xl >= wp - 1) { xh = xl = wp - 1; x = (float)xl; } else xh = xl + 1;
+        const float ly = yy - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+        acc += hy * hx * f[(size_t)(yl * wp + xl) * C + c] + hy * lx * f[(size_t)(yl * wp + xh) * C + c] +
+               ly * hx * f[(size_t)(yh * wp + xl) * C + c] + ly * lx * f[(size_t)(yh * wp + xh) * C + c];
+      }
+    }
+    out[((size_t)r * pooled * pooled + bin) * C + c] = acc / cnt;
+  }
+}
+}  // namespace
+
+// feats [n_img, hp*wp, C] f32 token-major (image stride feat_img_stride floats), rois [n_roi, 5] = (image, x1, y1, x2, y2) in
+// pixels, spatial scale 1/stride -> out [n_roi, pooled*pooled, C] f32.
+extern "C" int as_roi_align_tokens(const float* feats, long long feat_img_stride, const float* rois, int n_roi, int hp, int wp,
+                                   int C, int pooled, float spatial_scale, float* out, cudaStream_t stream) {
+  if (n_roi <= 0) return 0;
+  if (pooled < 1 || pooled > 32 || hp < 1 || wp < 1 || C < 1) return AS_ERR_BAD_ARG;
+  roi_align_tokens_kernel<<<dim3(pooled * pooled, n_roi), 128, 0, stream>>>(feats, feat_img_stride, rois, hp, wp, C, pooled, spatial_scale, out);
+  AS_LAUNCH_CHECK();
+  return 0;
+}

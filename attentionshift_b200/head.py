@@ -101,7 +101,7 @@ class AttnShiftRoIHead(nn.Module):
             pgt.append(g_i)
         return pos, pgt
 
-    def _mil_select(self, boxes, n_per_img, gt_labels, roi_feature_map, img_metas):
+    def _mil_select(self, boxes, n_per_img, gt_labels, roi_feature_map, img_metas, feats=None, hp=None, wp=None):
         """RH:2308-2312: hand the per-layer pseudo boxes to the MIL head and take its layer choice.  boxes [L, n_tot, 4].
         ``mil_fn(boxes_per_img, gt_labels, roi_feature_map, img_metas)`` gets the boxes as the reference builds them (per
         image [n_i, L, 4], RH:2296-2306) and may return the layer index per instance (tensor or per-image list), a pair
@@ -112,7 +112,12 @@ class AttnShiftRoIHead(nn.Module):
             out = self.mil_fn(per_img, gt_labels, roi_feature_map, img_metas)
         else:                                   # own MIL head (a bound dispatch: survives deepcopy / pickling of the module)
             from . import mil as _mil
-            out = _mil.mil_select(self.mil_head, roi_feature_map, per_img, gt_labels, self._mil_stride, self._mil_rsize)
+            if roi_feature_map is None and feats is not None and feats.is_cuda and not torch.is_grad_enabled():
+                # no feature map handed over and nothing to train (pseudo-label generation under no_grad): the selection runs on
+                # this repo's kernels, on the ViT tokens themselves = the reference's roi_skip_fpn=True feature map (CFG:58, DETB:122-127)
+                out = _mil.mil_select_device(self.mil_head, feats, per_img, gt_labels, hp, wp, self._mil_stride, self._mil_rsize)[0]
+            else:
+                out = _mil.mil_select(self.mil_head, roi_feature_map, per_img, gt_labels, self._mil_stride, self._mil_rsize)
         losses = {}
         if isinstance(out, tuple) and len(out) == 3:
             _, losses, idx = out
@@ -203,7 +208,7 @@ class AttnShiftRoIHead(nn.Module):
         if gt_index is None:
             if self.mil_fn is None and not hasattr(self, 'mil_head'):
                 raise ValueError('seed_pseudo_gt needs gt_index= or a mil_fn (MIL head is outside the hot path)')
-            gt_index, mil_losses = self._mil_select(boxes, n_per_img, labels, roi_feature_map, img_metas)
+            gt_index, mil_losses = self._mil_select(boxes, n_per_img, labels, roi_feature_map, img_metas, feats, hp, wp)
             begun = AS.refined_maps_begin(cams[gt_index, ar].contiguous(), mm[gt_index, ar].contiguous(), n_per_img, hp, wp)
         pseudo_boxes = boxes[gt_index, ar].contiguous()                # RH:2965-2967 gather of the chosen layer's box
         # A8, A13

@@ -114,3 +114,59 @@ def mil_select(mil_head, feature_map, boxes_per_img, gt_labels, stride=16, roi_s
     feats = roi_align(fmap, rois, roi_size, spatial_scale=1.0 / stride, sampling_ratio=0, aligned=True)
     idx, loss = mil_head(feats, gt_labels=gt_labels)
     return list(idx.split([int(b.shape[0]) for b in boxes_per_img], dim=0)), {'mil_loss': loss}
+
+
+def _pad_cols(t, mult=64):
+    k = t.shape[1]
+    kp = (k + mult - 1) // mult * mult
+    if kp == k:
+        return t.contiguous()
+    out = t.new_zeros(t.shape[0], kp)
+    out[:, :k] = t
+    return out
+
+
+@torch.no_grad()
+def mil_select_device(mil_head, feats, boxes_per_img, gt_labels, hp, wp, stride=16, roi_size=7):
+    """The selection half of ``_mil_forward_train`` (RH:2953-2972) on this repo's kernels, for calls that do not train the MIL
+    head (inference, frozen head, ``torch.no_grad()``): RoIAlign on the token-major feature map (``as_roi_align_tokens`` -- no
+    [B,C,Hp,Wp] transpose), LayerNorm -> fp16, ``decoder_embed`` / ``fc1`` / ``fc2`` / both branches on the tcgen05 GEMM (fp16
+    operands, fp32 accumulate; the two 20-class branches share one GEMM), the softmaxes / gather / arg-max of MIL:155-161 on the
+    [n_inst, L, classes] scores in torch.  feats [B, hp*wp, C] fp32; boxes_per_img: per image [n_i, L, 4].
+    -> per-image list of layer indices.  (The training call keeps ``mil_select``: its loss needs autograd.)"""
+    from . import lib as _l
+    from . import ops
+    L = _l.load()
+    dev = feats.device
+    rois = boxes_to_rois(boxes_per_img).float().to(dev).contiguous()
+    R, C = rois.shape[0], feats.shape[2]
+    x = torch.empty(R, roi_size * roi_size, C, device=dev, dtype=torch.float32)
+    assert feats.dtype == torch.float32 and feats.stride(2) == 1 and feats.stride(1) == C
+    _l.check(L.as_roi_align_tokens(_l.ptr(feats) if feats.is_contiguous() else __import__('ctypes').c_void_p(feats.data_ptr()),
+                                   feats.stride(0), _l.ptr(rois), R, hp, wp, C, roi_size, 1.0 / stride, _l.ptr(x), _l.stream_ptr()),
+             'as_roi_align_tokens')
+    h = lambda p: p.detach().half().contiguous()
+    t = x.view(R * roi_size * roi_size, C)
+    if mil_head.with_decoder_embed:
+        t = ops.layernorm_f16(t, mil_head.norm.weight.detach(), mil_head.norm.bias.detach(), mil_head.norm.eps)
+        t = ops.linear_f16(_pad_cols(t), _pad_cols(h(mil_head.decoder_embed.weight)), mil_head.decoder_embed.bias.detach().float(), ops.EPI_F16)
+    else:
+        t = t.half()
+    t = t.reshape(R, -1)
+    t = torch.relu(ops.linear_f16(_pad_cols(t), _pad_cols(h(mil_head.fc1.weight)), mil_head.fc1.bias.detach().float(), ops.EPI_F32)).half()
+    t = torch.relu(ops.linear_f16(_pad_cols(t), _pad_cols(h(mil_head.fc2.weight)), mil_head.fc2.bias.detach().float(), ops.EPI_F32)).half()
+    K = mil_head.num_classes
+    w = torch.cat((mil_head.classification_branch.weight, mil_head.proposal_branch.weight)).detach()
+    b = torch.cat((mil_head.classification_branch.bias, mil_head.proposal_branch.bias)).detach().float()
+    n_out = (2 * K + 31) // 32 * 32                                  # the GEMM writes whole 32-column groups
+    wp_ = w.new_zeros(n_out, w.shape[1]); wp_[:2 * K] = w
+    bp_ = b.new_zeros(n_out); bp_[:2 * K] = b
+    s = ops.linear_f16(_pad_cols(t), _pad_cols(wp_.half()), bp_, ops.EPI_F32)
+    Lq = mil_head.num_layers_query
+    cls = s[:, :K].reshape(-1, Lq, K).softmax(-1)                     # MIL:155-156
+    prop = s[:, K:2 * K].reshape(-1, Lq, K).softmax(-2)
+    bag = cls * prop
+    labels = torch.cat(list(gt_labels)) if isinstance(gt_labels, (list, tuple)) else gt_labels
+    score = torch.gather(bag, dim=-1, index=labels.to(dev).reshape(-1, 1, 1).repeat(1, Lq, 1))[..., 0]
+    idx = score.max(-1)[1]
+    return list(idx.split([int(b_.shape[0]) for b_ in boxes_per_img], dim=0)), score

@@ -221,6 +221,12 @@ int as_mean_shift_v2(const float* feats, long long feat_img_stride, int n_img, i
                      float* proto, float* sim_out, int n_shift, double tau0, double temp, int clamp0, int* trace,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* RoIAlign of the MIL layer selection (RH:2953-2972 -> mmcv RoIAlign, CFG:64-68: 7 x 7, sampling_ratio 0, aligned) on the
+ * token-major feature map: feats [n_img, hp*wp, C] f32, rois [n_roi,5] = (image, x1, y1, x2, y2) px -> out [n_roi, pooled^2, C]
+ * f32, the row layout MAEBoxHeadMIL's LayerNorm / decoder_embed consume (MIL:146-150). */
+int as_roi_align_tokens(const float* feats, long long feat_img_stride, const float* rois, int n_roi, int hp, int wp, int C,
+                        int pooled, float spatial_scale, float* out, as_stream_t stream);
+
 /* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
 
 int as_filter_seeds(const float* sim, const float* fg_low, int n_tot, int S, int N, float pos_thr, int* keep,
