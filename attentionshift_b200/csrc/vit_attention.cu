@@ -792,8 +792,13 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   float2* ml_s = reinterpret_cast<float2*>(smem + HM2_SMEM_TILES + 256);
   float* stage_s = reinterpret_cast<float*>(smem + HM2_SMEM_TILES + 256 + HM_MAX_HEADS * BQ * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Contiguous tile ranges per CTA.  (Dealing the tiles round-robin -- the whole grid on a few query-tile rows of ONE image at a
+  // time, so that the live Q / K set is one image's instead of the batch's -- was measured in round 2: DRAM reads do drop, but
+  // the row statistics are then reloaded for every tile behind two 512-thread barriers and the pass got 30 % SLOWER
+  // (3.30 -> 4.31 ms per step); the kernel is MUFU-bound, not DRAM-bound.)
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
+  const int my_tiles = max(tile1 - tile0, 0);
   const int nt = p.ntile;
 
   if (warp == 0 && lane == 0) {
@@ -813,7 +818,8 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       uint32_t g = 0;
       // every (q-tile, k-tile) re-reads the Q / K tiles of all heads: keep them in L2 against the output streams
       const uint64_t keep = l2_policy_evict_last();
-      for (int tile = tile0; tile < tile1; ++tile) {
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = tile0 + ti;
         const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
         for (int h = 0; h < p.heads; ++h, ++g) {
           const uint32_t st = g % HM2_STAGES;
@@ -826,7 +832,7 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_s = umma_idesc(0, BQ, BKV);
-    const uint32_t total = (uint32_t)max(tile1 - tile0, 0) * (uint32_t)p.heads;
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.heads;
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t st = g % HM2_STAGES, tb = g % HM2_NBUF;
       mbar_wait(&full[st], (g / HM2_STAGES) & 1);
@@ -851,7 +857,8 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     uint32_t g = 0;
     int cur_bq = -1;
     const uint64_t stream_out = l2_policy_evict_first();   // the maps are written once and read by a later kernel
-    for (int tile = tile0; tile < tile1; ++tile) {
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int tile = tile0 + ti;
       const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
       const int t = qt * BQ + row;
       if (b * nt + qt != cur_bq) {                     // new query tile: softmax row statistics of all heads -> smem

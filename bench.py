@@ -231,6 +231,15 @@ def count_launches(fn):
         return None, None
 
 
+def pregrow_allocator(dev, mib=96):
+    """Give torch's caching allocator a cushion of small-pool segments before the timed regions.  The head allocates a few hundred
+    small tensors per step; whenever their live set exceeds what the small pool has cached, the allocator grows it by one 2 MiB
+    segment = a cudaMalloc in the middle of a step, which showed up as ONE 40-110 ms step in some runs of ten
+    (`e2e.allocator_growth_mib` reports any growth that still happens inside the timed e2e region)."""
+    hold = [torch.empty(512 * 1024, device=dev, dtype=torch.uint8) for _ in range(2 * mib)]
+    del hold
+
+
 def time_steps(fn, steps, barrier, per_step=None):
     """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream.  ``per_step``: list that
     receives the individual step times (an event after every step: no synchronisation, the timed region is unchanged)."""
@@ -302,6 +311,7 @@ def run_ours(args):
     for _ in range(warm):
         one_step(bb, head, img_dev, inputs, False)
     torch.cuda.synchronize()
+    pregrow_allocator(dev)
 
     # ---- device-resident timing (value): library timing slots OFF, nothing but the step's own work on the stream
     if sampler is not None:
@@ -322,7 +332,7 @@ def run_ours(args):
             bufs[i % 2].copy_(img_host, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
-    def e2e_loop(n):
+    def e2e_loop(n, marks=None):
         d2h = 0
         prefetch(0)
         for i in range(n):
@@ -332,6 +342,8 @@ def run_ours(args):
             res = one_step(bb, head, bufs[i % 2], inputs, True)
             freed[i % 2].record()
             d2h = sum(m.nbytes for m in res['pseudo_gt_masks'])
+            if marks is not None:
+                marks[i + 1].record()
         return d2h
 
     for f in freed:
@@ -341,12 +353,17 @@ def run_ours(args):
     gc.disable()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    mem0 = torch.cuda.memory_reserved()
     e2.record()
-    d2h = e2e_loop(args.steps)
+    marks[0].record()
+    d2h = e2e_loop(args.steps, marks)
     e3.record()
     barrier()
     gc.enable()
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    e2e_step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(args.steps)]
+    mem_growth_mib = (torch.cuda.memory_reserved() - mem0) / 2 ** 20
     if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -438,7 +455,8 @@ def run_ours(args):
                                          'produced as roll-out operands (attn_layers=7, attn_format=rollout)',
                                 kernel_times='library timing slots, separate untimed pass after the timed regions', small=bool(args.small)),
                     e2e=dict(value=round(world * B / (ms_e2e * 1e-3), 2), unit='images/s', ms_per_step=round(ms_e2e, 3),
-                             h2d_bytes_per_step=int(img_host.nbytes), d2h_bytes_per_step=int(d2h)),
+                             h2d_bytes_per_step=int(img_host.nbytes), d2h_bytes_per_step=int(d2h), step_ms=e2e_step_ms,
+                             allocator_growth_mib=round(mem_growth_mib, 1)),
                     gpu_launches=n_ours, all_launches=n_all, clocks=sampler.summary() if sampler is not None else None, roofline=roof, roofline_attnshift=roof2,
                     reference_config=ref_cfg,
                     kernel_ms_per_step={k: round(v['ms'], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])})
