@@ -626,6 +626,7 @@ struct HmParams {
   int ldt;
   float t_scale;
   int qt0, nqt;               // query tiles [qt0, qt0 + nqt) are produced (persistent schedule only); default: all
+  int per_image;              // tile order of the persistent schedule (see the kernel)
 };
 
 __global__ void __launch_bounds__(HM_THREADS, 1)
@@ -796,10 +797,18 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // time, so that the live Q / K set is one image's instead of the batch's -- was measured in round 2: DRAM reads do drop, but
   // the row statistics are then reloaded for every tile behind two 512-thread barriers and the pass got 30 % SLOWER
   // (3.30 -> 4.31 ms per step); the kernel is MUFU-bound, not DRAM-bound.)
+  // p.per_image (env AS_HEADMEAN_ORDER=image, experiment): every image's tiles are split contiguously over the grid and the images
+  // are walked one after the other, so the grid works on ONE image at a time (live set = its Q and K, 13 MB) while a CTA still
+  // sweeps consecutive key tiles of a query row.  Measured: 0.643 ms vs 0.557 ms for the default order (roll-out operands only,
+  // profiles/microbench_headmean_r3.txt) -- the statistics reloads cost more than the DRAM reads they save; not the default.
+  const int nt = p.ntile;
+  const int per_img = p.nqt * nt;
+  const int img_lo = (int)((long long)blockIdx.x * per_img / gridDim.x), img_hi = (int)((long long)(blockIdx.x + 1) * per_img / gridDim.x);
+  const int img_cnt = img_hi - img_lo;
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
-  const int my_tiles = max(tile1 - tile0, 0);
-  const int nt = p.ntile;
+  const int my_tiles = p.per_image ? (n_tiles / per_img) * img_cnt : max(tile1 - tile0, 0);
+  auto tile_of = [&](int ti) { return p.per_image ? (ti / img_cnt) * per_img + img_lo + ti % img_cnt : tile0 + ti; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
@@ -819,7 +828,7 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // every (q-tile, k-tile) re-reads the Q / K tiles of all heads: keep them in L2 against the output streams
       const uint64_t keep = l2_policy_evict_last();
       for (int ti = 0; ti < my_tiles; ++ti) {
-        const int tile = tile0 + ti;
+        const int tile = tile_of(ti);
         const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
         for (int h = 0; h < p.heads; ++h, ++g) {
           const uint32_t st = g % HM2_STAGES;
@@ -858,7 +867,7 @@ attn_headmean2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     int cur_bq = -1;
     const uint64_t stream_out = l2_policy_evict_first();   // the maps are written once and read by a later kernel
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int tile = tile0 + ti;
+      const int tile = tile_of(ti);
       const int b = tile / (p.nqt * nt), r = tile - b * p.nqt * nt, qt = p.qt0 + r / nt, kt = r % nt;
       const int t = qt * BQ + row;
       if (b * nt + qt != cur_bq) {                     // new query tile: softmax row statistics of all heads -> smem
@@ -1056,6 +1065,11 @@ extern "C" int as_attn_headmean_ex(const void* q, const void* k, const float* m,
   p.t_hi = (__half*)t_hi; p.t_lo = (__half*)t_lo; p.ldt = ldt; p.t_scale = t_scale;
   const int nt = (T + BQ - 1) / BQ;
   p.qt0 = q_row0 / BQ; p.nqt = nt - p.qt0;
+  {
+    static int order = -1;                   // env AS_HEADMEAN_ORDER=image: per-image tile order (experiment)
+    if (order < 0) { const char* e = getenv("AS_HEADMEAN_ORDER"); order = (e && e[0] == 'i') ? 1 : 0; }
+    p.per_image = order;
+  }
   if (rowsum_slices == 4) {
     if (ld % 4 || ld < nt * BKV) return AS_ERR_BAD_ARG;   // float4 row stores, whole 128-column tiles
     const int n_tiles = p.nqt * nt * B;
