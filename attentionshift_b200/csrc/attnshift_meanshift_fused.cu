@@ -28,6 +28,7 @@
 //                  (generic stores, fence.proxy.async + the group barrier make them visible to the other CTAs' TMA)
 //   -- group barrier --
 // and one more affinity pass (unmasked) for the returned similarity maps.  All reductions are ordered: deterministic.
+#include <cstdlib>
 #include "common.cuh"
 #include <float.h>
 
@@ -65,6 +66,7 @@ __device__ __forceinline__ bool in_box(const Box& b, int n, int wp) {
 
 struct FusedParams {
   int n_img, N, C, hp, wp, S, G, n_shift, clamp0;
+  int blocked;                 // token copies stored as 8 x 8 patch blocks (hp, wp multiples of 8): a 64-token unit is one block
   float tt0, temp;
   const int* img_first; const int* img_nobj; const float* rois;
   const float* den;            // [n_img][N]   |f| (clamped at 1e-8)
@@ -145,6 +147,8 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   uint64_t* u_empty = bars + 16;     // U_STAGES
   uint64_t* upd_done = bars + 20;    // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint8_t* ok_s = reinterpret_cast<uint8_t*>(bars + 26);       // [TOK] is the CTA's local token a token of the image?
+  int* unit_act_s = reinterpret_cast<int*>(bars + 22);         // [4] does the 64-token unit hold a token inside any instance box?
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wt = threadIdx.x - 64;                            // worker thread id 0..255 (negative for warps 0, 1)
@@ -176,6 +180,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
   uint32_t acount = 0;                          // workers: affinity passes so far
   uint32_t ucount = 0;                          // producer + MMA: phase B stages so far
   uint32_t wcount = 0;                          // MMA + workers: update phases so far
+  uint32_t dcount = 0;                          // workers: update phases that issued MMAs (completed phases of upd_done)
 
   uint64_t t_prev = global_timer_ns();
   auto mark = [&](int k) {
@@ -193,15 +198,48 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
     const int kb_cols = nobj * p.S;
     // the CTA's 256 tokens are four 64-token units taken round-robin over the group (unit u of CTA q = global unit u*G + q):
     // every CTA sees all parts of the image, so box-shaped instance masks load the CTAs of a group evenly
-    auto tok = [&](int tl) { return ((tl >> 6) * p.G + q) * 64 + (tl & 63); };
+    // With blocked storage a unit is an 8 x 8 block of patches, so that whole units fall outside every instance box and are
+    // skipped (below); tok() is the token's index in the image either way.
+    const int wb = p.wp >> 3;
+    // unit u of CTA q = global unit u*G + (q + u*rot) % G: the rotation spreads a CTA's four blocks over the block columns,
+    // so a box loads the CTAs of a group evenly
+    const int rot = p.blocked ? p.G / 4 + 1 : 0;
+    auto unit_of = [&](int u) { return u * p.G + (q + u * rot) % p.G; };
+    auto tok = [&](int tl) {
+      const int unit = unit_of(tl >> 6), t = tl & 63;
+      if (!p.blocked) return unit * 64 + t;
+      const int by = unit / wb, bx = unit - by * wb;
+      return (by * 8 + (t >> 3)) * p.wp + bx * 8 + (t & 7);
+    };
     unsigned* ctr = p.bar + img;
     unsigned bar_target = 0;
     float fmax_cta = 1.f;
+    // per-thread token indices of the image (index arithmetic hoisted out of the passes): n_wt for local token wt, n_tl / box
+    // membership bits for the token whose affinity row this thread reads back from TMEM
+    int n_wt = 0, n_tl = 0;
+    unsigned inmask_tl = 0, inmask_wt = 0;
     if (wt >= 0) {
-      const int n = tok(wt);
+      n_wt = tok(wt);
+      n_tl = tok(((warp - 2) >> 2) * 128 + (warp & 3) * 32 + lane);
+      if (n_tl < p.N)
+        for (int j = 0; j < nobj; ++j)
+          if (in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n_tl, p.wp)) inmask_tl |= 1u << j;
+      if (n_wt < p.N)
+        for (int j = 0; j < nobj; ++j)
+          if (in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n_wt, p.wp)) inmask_wt |= 1u << j;
+      ok_s[wt] = n_wt < p.N;
+    }
+    if (wt >= 0) {
+      const int n = n_wt;
       const float dn = n < p.N ? p.den[(size_t)img * p.N + n] : 1.f;
       den_s[wt] = dn;
       for (int j = 0; j < MAXOBJ; ++j) { idx_s[j * TOK + wt] = -1; w_s[j * TOK + wt] = 0.f; }
+      // A 64-token unit none of whose tokens lies in any instance box contributes exact zeros to the masked affinity and to the
+      // update (the reference multiplies those tokens by zero, RH:1824): its token tiles are neither loaded nor multiplied in the
+      // masked passes.  (The last, unmasked pass reads every unit.)
+      if (wt < 4) unit_act_s[wt] = 0;
+      workers_sync();
+      if (__any_sync(0xffffffffu, inmask_wt != 0) && lane == 0) atomicOr(&unit_act_s[wt >> 6], 1);
       // largest token norm of this CTA (bounds weight x |f| for the power-of-two scaling of the update's weight tiles)
       const float wm = warp_max(dn);
       if (lane == 0) red_s[warp - 2] = wm;
@@ -298,6 +336,9 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
     bar_target += p.G;
     group_barrier(ctr, bar_target);
     mark(0);
+    const unsigned umask = (unit_act_s[0] ? 1u : 0u) | (unit_act_s[1] ? 2u : 0u) | (unit_act_s[2] ? 4u : 0u) | (unit_act_s[3] ? 8u : 0u);
+    auto uact = [&](int u) { return ((umask >> u) & 1u) != 0; };
+    const bool any_unit = umask != 0;
 
     for (int it = 0; it <= p.n_shift; ++it) {
       const bool last = (it == p.n_shift);                    // extra pass: unmasked similarities for the output
@@ -305,7 +346,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
       if (warp == 0) {
         if (lane == 0) {
           fence_proxy_async_all();
-          for (int kb = 0; kb < kblocks; ++kb) {
+          for (int kb = 0; kb < kblocks && (last || any_unit); ++kb) {
             const uint32_t bb = bcount & 1;
             mbar_wait(&b_empty[bb], ((bcount >> 1) & 1) ^ 1);
             mbar_expect_tx(&b_full[bb], B_TILE);
@@ -313,10 +354,13 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
             tma_load_3d(ring + 3 * A_STAGE + bb * B_TILE + 8192, &tm_plo, &b_full[bb], kb * 64, 0, img);
             ++bcount;
             for (int mt = 0; mt < 2; ++mt) {
+              const bool a0 = last || uact(2 * mt), a1 = last || uact(2 * mt + 1);
+              if (!a0 && !a1) continue;                       // the whole 128-row tile is outside every box
               mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-              mbar_expect_tx(&a_full[a_stage], A_STAGE);
+              mbar_expect_tx(&a_full[a_stage], (a0 ? 16384 : 0) + (a1 ? 16384 : 0));
               for (int h = 0; h < 2; ++h) {                   // a 128-row operand tile = two 64-token units
-                const int row0 = ((2 * mt + h) * p.G + q) * 64;
+                if (!(h ? a1 : a0)) continue;                 // stale rows of a skipped unit are masked to zero by the epilogue
+                const int row0 = unit_of(2 * mt + h) * 64;
                 tma_load_3d(ring + a_stage * A_STAGE + h * 8192, &tm_hi64, &a_full[a_stage], kb * 64, row0, img);
                 tma_load_3d(ring + a_stage * A_STAGE + 16384 + h * 8192, &tm_lo64, &a_full[a_stage], kb * 64, row0, img);
               }
@@ -326,10 +370,13 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
         }
       } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc(0, 128, LDK);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const bool t0 = last || uact(0) || uact(1), t1 = last || uact(2) || uact(3);     // which 128-row tiles take part
+        const int mt_last = t1 ? 1 : 0;
+        for (int kb = 0; kb < kblocks && (t0 || t1); ++kb) {
           const uint32_t bb = bcount & 1;
           mbar_wait(&b_full[bb], (bcount >> 1) & 1);
           for (int mt = 0; mt < 2; ++mt) {
+            if (!(mt ? t1 : t0)) continue;
             mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
             if (elect_one()) {
@@ -342,8 +389,8 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
                 mma_f16_ss(tmem + mt * LDK, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1);
               }
               tc_commit(&a_empty[a_stage]);
-              if (mt == 1) tc_commit(&b_empty[bb]);
-              if (mt == 1 && kb == kblocks - 1) tc_commit(acc_full);
+              if (mt == mt_last) tc_commit(&b_empty[bb]);
+              if (mt == mt_last && kb == kblocks - 1) tc_commit(acc_full);
             }
             __syncwarp();
             if (++a_stage == 3) { a_stage = 0; a_phase ^= 1; }
@@ -355,18 +402,23 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
         {
           const int quad = warp & 3, mt = (warp - 2) >> 2;
           const int tl = mt * 128 + quad * 32 + lane;
-          const int n = tok(tl);
-          unsigned inmask = 0;                                // bit j: token inside instance j's box (all ones on the last pass)
-          if (n < p.N)
-            for (int j = 0; j < nobj; ++j)
-              if (last || in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n, p.wp)) inmask |= 1u << j;
-          mbar_wait(acc_full, acount & 1);
+          // bit j: token inside instance j's box (all ones on the last pass)
+          unsigned inmask = n_tl < p.N ? (last ? 0xffffffffu : inmask_tl) : 0u;
+          const bool pass_ran = last || any_unit;             // (uniform over the CTA) were any MMAs issued in this pass?
+          const bool tile_ran = last || uact(2 * mt) || uact(2 * mt + 1);
+          if (pass_ran) mbar_wait(acc_full, acount & 1);
           tc_fence_after();
           mark(10);
           uint32_t v0[32], v1[32];
-          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK, v0);
-          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK + 32, v1);
-          tc_wait_ld();
+          if (tile_ran) {
+            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK, v0);
+            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + mt * LDK + 32, v1);
+            tc_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v0[i] = v1[i] = 0u;
+            inmask = 0;
+          }
           const float alpha = 1.f / (OP_SCALE * OP_SCALE);
           float* row = sims_s + tl * SIM_LD;
           int j = 0, s = 0;
@@ -378,11 +430,11 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
           }
           tc_fence_before();
         }
-        ++acount;
+        if (last || any_unit) ++acount;                       // acc_full completed a phase only if the pass issued MMAs
         workers_sync();
         if (last) {
           // returned maps [o][s][n]: one coalesced row of this CTA's tokens per seed
-          const int n = tok(wt);
+          const int n = n_wt;
           if (n < p.N)
             for (int col = 0; col < kb_cols; ++col) {
               float v = sims_s[wt * SIM_LD + col];
@@ -397,7 +449,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
             const int j = col / p.S, s = col - j * p.S;
 #pragma unroll 8
             for (int t = g4; t < TOK; t += 4) {
-              const bool ok = tok(t) < p.N;
+              const bool ok = ok_s[t] != 0;
               const float v = sims_s[t * SIM_LD + col];
               mx = ok ? fmaxf(mx, v) : mx;
               const bool hit = ok && it > 0 && idx_s[j * TOK + t] == s;
@@ -450,7 +502,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
           for (int t = g4; t < TOK; t += 4) {
             const float e = expf((sims_s[t * SIM_LD + col] - cmax) * inv_tt);
             sims_s[t * SIM_LD + col] = e;                       // the assignment only needs weight = e / Z: no second exp
-            z += tok(t) < p.N ? e : 0.f;
+            z += ok_s[t] ? e : 0.f;
           }
         }
         red_s[wt] = z;
@@ -472,11 +524,12 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
           // L2 still holds
           for (int cb = cblocks - 1; cb >= 0; --cb)
             for (int u = 0; u < 4; ++u) {
+              if (!uact(u)) continue;                         // every weight of the unit is zero
               const uint32_t st = ucount % U_STAGES;
               mbar_wait(&u_empty[st], ((ucount / U_STAGES) & 1) ^ 1);
               mbar_expect_tx(&u_full[st], U_STAGE);
               uint8_t* dst = ring + st * U_STAGE;
-              const int row0 = (u * p.G + q) * 64;
+              const int row0 = unit_of(u) * 64;
               tma_load_3d(dst, &tm_hi64, &u_full[st], (2 * cb) * 64, row0, img);
               tma_load_3d(dst + 8192, &tm_hi64, &u_full[st], (2 * cb + 1) * 64, row0, img);
               tma_load_3d(dst + 16384, &tm_lo64, &u_full[st], (2 * cb) * 64, row0, img);
@@ -489,8 +542,11 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
         constexpr uint32_t idesc_u = umma_idesc(0, 128, LDK) | (1u << 15);      // A is MN-major (channels contiguous)
         mbar_wait(w_full, wcount & 1);
         tc_fence_after();
+        const int u_first = uact(0) ? 0 : uact(1) ? 1 : uact(2) ? 2 : 3;
+        const int u_last = uact(3) ? 3 : uact(2) ? 2 : uact(1) ? 1 : 0;
         for (int cb = cblocks - 1; cb >= 0; --cb)
           for (int u = 0; u < 4; ++u) {
+            if (!uact(u)) continue;
             const uint32_t st = ucount % U_STAGES;
             mbar_wait(&u_full[st], (ucount / U_STAGES) & 1);
             tc_fence_after();
@@ -501,12 +557,12 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
               for (int k = 0; k < 4; ++k) {                   // 16 tokens per MMA = two 8-token swizzle atoms (SBO = 1024 B)
                 const uint64_t dah = umma_desc_mn_sw128(a_hi + k * 2048, 8192), dal = umma_desc_mn_sw128(a_lo + k * 2048, 8192);
                 const uint64_t dwh = umma_desc_k_sw128(w_hi + k * 32), dwl = umma_desc_k_sw128(w_lo + k * 32);
-                mma_f16_ss(tmem + TM_UPD + cb * LDK, dah, dwh, idesc_u, (u | k) != 0);
+                mma_f16_ss(tmem + TM_UPD + cb * LDK, dah, dwh, idesc_u, u != u_first || k != 0);
                 mma_f16_ss(tmem + TM_UPD + cb * LDK, dah, dwl, idesc_u, 1);
                 mma_f16_ss(tmem + TM_UPD + cb * LDK, dal, dwh, idesc_u, 1);
               }
               tc_commit(&u_empty[st]);
-              if (u == 3 && cb == 0) tc_commit(upd_done);
+              if (u == u_last && cb == 0) tc_commit(upd_done);
             }
             __syncwarp();
             ++ucount;
@@ -516,7 +572,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
         if (wt < kb_cols) st_s[wt * 4 + 2] = 1.f / sum_partials(p.z_part + (size_t)img * p.G * LDK + wt, LDK, p.G);    // fixed order
         workers_sync();
         {
-          const int n = tok(wt);
+          const int n = n_wt;
           const float* row = sims_s + wt * SIM_LD;
           for (int j = 0; j < nobj; ++j) {
             float best = -1.f;
@@ -533,7 +589,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
                 if (s + i < p.S && w4[i] > best) { best = w4[i]; bi = s + i; }     // first maximum wins (torch.argmax)
             }
             const bool valid = n < p.N;
-            const bool inside = valid && in_box(patch_box(p.rois + 4 * (o0 + j), p.hp, p.wp), n, p.wp);
+            const bool inside = (inmask_wt >> j) & 1u;
             idx_s[j * TOK + wt] = valid ? bi : -1;            // density of the next iteration counts every token
             w_s[j * TOK + wt] = inside ? best : 0.f;          // masked tokens are zero vectors: they add nothing
             if (p.trace && valid) p.trace[((size_t)it * p.n_tot + o0 + j) * p.N + n] = bi;
@@ -569,16 +625,21 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
         if (lane == 0) mbar_arrive(w_full);
         mark(5);
         // ---- update epilogue: TMEM -> partial prototypes [seed][channel] (lane = channel: coalesced rows)
-        mbar_wait(upd_done, wcount & 1);
         ++wcount;
+        if (any_unit) { mbar_wait(upd_done, dcount & 1); ++dcount; }
         tc_fence_after();
         {
           const int quad = warp & 3, half = (warp - 2) >> 2;
           for (int cb = half; cb < cblocks; cb += 2) {
             uint32_t v0[32], v1[32];
-            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK, v0);
-            tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK + 32, v1);
-            tc_wait_ld();
+            if (any_unit) {
+              tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK, v0);
+              tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + TM_UPD + cb * LDK + 32, v1);
+              tc_wait_ld();
+            } else {                                          // no token of this CTA lies in a box: its partial is zero
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v0[i] = v1[i] = 0u;
+            }
             float* dst = p.proto_part + ((size_t)img * p.G + q) * LDK * p.C + cb * 128 + quad * 32 + lane;
 #pragma unroll
             for (int col = 0; col < LDK; ++col) {                 // running pointer: one 64-bit add per row, no wide multiply
@@ -628,8 +689,8 @@ static unsigned long long* g_fused_dbg = nullptr;
 extern "C" void as_mean_shift_fused_debug(unsigned long long* buf) { g_fused_dbg = buf; }
 
 namespace {
-__global__ void fused_split_tokens(const float* __restrict__ feats, long long fstride, int N, int C, __half* __restrict__ hi,
-                                   __half* __restrict__ lo, float* __restrict__ den) {
+__global__ void fused_split_tokens(const float* __restrict__ feats, long long fstride, int N, int C, int wp, int blocked,
+                                   __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ den) {
   const int img = blockIdx.y;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -642,7 +703,12 @@ __global__ void fused_split_tokens(const float* __restrict__ feats, long long fs
   }
   const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-8f);
   if (lane == 0) den[(size_t)img * N + n] = nrm;
-  const size_t o = ((size_t)img * N + n) * C;
+  int pos = n;                                                 // row of the token in the split copies
+  if (blocked) {
+    const int y = n / wp, x = n - y * wp;
+    pos = ((y >> 3) * (wp >> 3) + (x >> 3)) * 64 + (y & 7) * 8 + (x & 7);
+  }
+  const size_t o = ((size_t)img * N + pos) * C;
   for (int c = lane * 4; c < C; c += 128) {
     const float4 t = *reinterpret_cast<const float4*>(f + c);
     const float x[4] = {t.x, t.y, t.z, t.w};
@@ -695,7 +761,9 @@ extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride
   AS_CUDA(cudaMemsetAsync(p.bar, 0, (size_t)n_img * 4, stream));
   AS_CUDA(cudaMemsetAsync(p.phat_hi, 0, (size_t)n_img * LDK * C * 2, stream));      // rows past an image's seed count stay zero
   AS_CUDA(cudaMemsetAsync(p.phat_lo, 0, (size_t)n_img * LDK * C * 2, stream));
-  fused_split_tokens<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, hi, lo, (float*)p.den);
+  p.blocked = (hp % 8 == 0 && wp % 8 == 0) ? 1 : 0;
+  if (const char* e = getenv("AS_MS_BLOCKED")) p.blocked = p.blocked && atoi(e) != 0;      // measurement switch (row units)
+  fused_split_tokens<<<dim3((N + 7) / 8, n_img), 256, 0, stream>>>(feats, feat_img_stride, N, C, wp, p.blocked, hi, lo, (float*)p.den);
 
   CUtensorMap tm[4];
   uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)n_img};
