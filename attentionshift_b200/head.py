@@ -71,6 +71,7 @@ class AttnShiftRoIHead(nn.Module):
         self.rng = rng if rng is not None else AS.KeyedRng(torch.initial_seed() & 0x7fffffff)
         self.with_mil = mil_head is not None or mil_fn is not None or hasattr(self, 'mil_head')
         self.with_deform_sup = False
+        self.device_matching = True             # match_points: device solver when the predictions live on the GPU
         self._mask_bufs = {}
 
     def _mask_buffer(self, shape):
@@ -87,10 +88,14 @@ class AttnShiftRoIHead(nn.Module):
 
     # ---- the two selections that sit next to the device path ---------------------------------------------
     def match_points(self, point_reg, point_cls, gt_points, gt_labels, imgs_wh):
-        """RH:2237-2257: the reference's HungarianPointAssigner + PointPseudoSampler per image (``assigner.py``; host + scipy
-        like the reference).  -> (pos_inds, pos_gt): per image the matched point tokens in ascending order and the GT each
-        one belongs to."""
-        from .assigner import hungarian_point_assign
+        """RH:2237-2257: the reference's HungarianPointAssigner + PointPseudoSampler per image.  -> (pos_inds, pos_gt): per
+        image the matched point tokens in ascending order and the GT each one belongs to.  Predictions on the GPU: the whole
+        batch is matched on the device (``as_hungarian_points``, the solver scipy runs, without the reference's ``cost.cpu()``
+        round trip); host tensors (or ``device_matching = False``) take the reference's route, scipy on the host."""
+        from .assigner import hungarian_point_assign, hungarian_point_assign_device
+        if point_reg.is_cuda and self.device_matching:
+            return hungarian_point_assign_device(point_reg, point_cls, gt_points, gt_labels, imgs_wh, self.point_cls_weight,
+                                                 self.point_reg_weight)
         reg = point_reg.detach().float().cpu()
         cls = point_cls.detach().float().cpu()
         pos, pgt = [], []

@@ -50,6 +50,7 @@ SIGNATURES = {
     'as_mean_shift_v2_occupancy': (_i, [_vp, _vp, _vp]),
     'as_mean_shift_v2': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_roi_align_tokens': (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    'as_hungarian_points': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'as_cosine_maps_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'as_cosine_maps': (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'as_rollout_workspace': (_sz, [_i, _i, _i]),

@@ -227,6 +227,18 @@ int as_mean_shift_v2(const float* feats, long long feat_img_stride, int n_img, i
 int as_roi_align_tokens(const float* feats, long long feat_img_stride, const float* rois, int n_roi, int hp, int wp, int C,
                         int pooled, float spatial_scale, float* out, as_stream_t stream);
 
+/* ------------------------------------------------------------------ point-token <-> GT matching (RH:2237-2257)
+ * Replaces HungarianPointAssigner.assign's host hop (mmdet/core/bbox/assigners/hungarian_point_assigner.py:95-99: cost.cpu()
+ * + scipy.optimize.linear_sum_assignment) followed by PointPseudoSampler (point_pseudo_sampler.py:34-37).
+ * cost [sum_i G_i, P] f32 row-major: one row of proposal costs per GT (the transpose of assign()'s [P, G_i] matrix,
+ * match_cost.py:56-58,90-106), GTs in image order (image i owns rows g_first[i] .. g_first[i] + g_count[i]); max_g >= every
+ * g_count.  Writes, per image, the
+ * min(P, G_i) matched proposals in ascending order to pos_inds[g_first[i] + k] and the GT of each to pos_gt[g_first[i] + k].
+ * status [n_img] (may be null): 1 = the matrix held NaN / -inf or no finite matching exists (scipy raises ValueError there);
+ * the outputs are then the identity pairing.  fp64 shortest-augmenting-path search, one warp per image; P, max_g <= 512. */
+int as_hungarian_points(const float* cost, const int* g_first, const int* g_count, int n_img, int P, int max_g,
+                        int* pos_inds, int* pos_gt, int* status, as_stream_t stream);
+
 /* ------------------------------------------------------------------ part discovery (RH:265-301, RH:222-262) */
 
 int as_filter_seeds(const float* sim, const float* fg_low, int n_tot, int S, int N, float pos_thr, int* keep,
