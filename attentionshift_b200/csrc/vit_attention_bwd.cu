@@ -38,7 +38,25 @@ struct BwdParams {
   const float* delta;                      // [BH, T] rowsum(dO o O)
   float* out0;                             // dkv: dK [BH, T, 64];  dq: dQ [BH, T, 64]
   float* out1;                             // dkv: dV [BH, T, 64]
+  __half* qkv16;                           // optional: dQ | dK | dV as fp16 rows of the qkv Linear's output [B*T, 3*heads*64]
 };
+
+// 32 gradient values of one (token, head) -> fp16, at their place in the qkv Linear's output row (VT:76: column =
+// which * C + head * 64 + d), so that the projection's dX / dW GEMMs read them without a layout pass
+__device__ __forceinline__ void store_qkv16(const BwdParams& p, const uint32_t (&a)[32], int bh, int t, int which, int half32) {
+  const int b = bh / p.heads, h = bh - b * p.heads, C = p.heads * HD;
+  uint4* dst = reinterpret_cast<uint4*>(p.qkv16 + ((size_t)b * p.T + t) * (3 * C) + which * C + h * HD + half32 * 32);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hh = __floats2half2_rn(__uint_as_float(a[8 * g + 2 * e]), __uint_as_float(a[8 * g + 2 * e + 1]));
+      w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 
 __device__ __forceinline__ int sw128p(int row, int col) {      // byte offset of (row, col) in a [rows x 64 halves] swizzled block
   return row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1);
@@ -240,10 +258,13 @@ mhsa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_32x32(tm_row + (ch < 2 ? C_ACC0 : C_ACC1) + hf * 32, a);
       tc_wait_ld();
       if (kr < p.T) {
-        float4* dst = reinterpret_cast<float4*>((ch < 2 ? p.out0 : p.out1) + ((size_t)bh * p.T + kr) * HD + hf * 32);
+        if (p.qkv16) store_qkv16(p, a, bh, kr, ch < 2 ? 1 : 2, hf);
+        else {
+          float4* dst = reinterpret_cast<float4*>((ch < 2 ? p.out0 : p.out1) + ((size_t)bh * p.T + kr) * HD + hf * 32);
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          dst[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+          for (int g = 0; g < 8; ++g)
+            dst[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+        }
       }
     }
     tc_fence_before();
@@ -385,10 +406,13 @@ mhsa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tmem_ld_32x32(tm_row + C_ACC0 + ch * 32, a);
       tc_wait_ld();
       if (ok) {
-        float4* dq = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + t) * HD + ch * 32);
+        if (p.qkv16) store_qkv16(p, a, bh, t, 0, ch);
+        else {
+          float4* dq = reinterpret_cast<float4*>(p.out0 + ((size_t)bh * p.T + t) * HD + ch * 32);
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          dq[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+          for (int g = 0; g < 8; ++g)
+            dq[g] = make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]));
+        }
       }
     }
     tc_fence_before();
@@ -417,10 +441,12 @@ int enc_transposed(CUtensorMap* tm, const void* base, int BH, int Tpad) {  // [B
 // [B, heads, 64, Tpad] fp16 with zero padding (Tpad = T rounded up to 128); m, l: the forward's row statistics [B, heads, T];
 // delta [B, heads, T] = rowsum(dO o O).  Outputs dq, dk, dv [B, heads, T, 64] fp32 (gradients w.r.t. the UNSCALED q, k: the
 // head_dim^-0.5 factor of VT:79 is applied inside).
-extern "C" int as_mhsa_bwd(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
-                           const void* dot, const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv,
-                           int B, int T, int Tpad, int heads, cudaStream_t stream) {
-  if (Tpad % BT || Tpad < T || T < 1) return AS_ERR_BAD_ARG;
+// as_mhsa_bwd_ex: ``dqkv16`` non-null -> the three gradients are written as fp16 into one [B*T, 3*heads*64] tensor laid out
+// like the qkv Linear's output (the operand of its dX / dW GEMMs) and dq / dk / dv are not touched.
+extern "C" int as_mhsa_bwd_ex(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                              const void* dot, const float* m, const float* l, const float* delta, float* dq, float* dk,
+                              float* dv, void* dqkv16, int B, int T, int Tpad, int heads, cudaStream_t stream) {
+  if (Tpad % BT || Tpad < T || T < 1 || (!dqkv16 && (!dq || !dk || !dv))) return AS_ERR_BAD_ARG;
   const int BH = B * heads;
   CUtensorMap tq, tk, tv, tdo, tqt, tkt, tdot;
   int r = enc_rows(&tq, q, BH, T);
@@ -440,7 +466,7 @@ extern "C" int as_mhsa_bwd(const void* q, const void* k, const void* v, const vo
   BwdParams p;
   p.T = T; p.heads = heads; p.nt = (T + BT - 1) / BT;
   p.scale = 0.125f; p.scale_log2 = (float)(0.125 * 1.4426950408889634);
-  p.m = m; p.l = l; p.delta = delta;
+  p.m = m; p.l = l; p.delta = delta; p.qkv16 = (__half*)dqkv16;
   const dim3 grid(p.nt, heads, B);
   p.out0 = dk; p.out1 = dv;
   mhsa_bwd_dkv_kernel<<<grid, BWD_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tqt, tdot, p);
@@ -448,4 +474,10 @@ extern "C" int as_mhsa_bwd(const void* q, const void* k, const void* v, const vo
   mhsa_bwd_dq_kernel<<<grid, BWD_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, tkt, p);
   AS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int as_mhsa_bwd(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                           const void* dot, const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv,
+                           int B, int T, int Tpad, int heads, cudaStream_t stream) {
+  return as_mhsa_bwd_ex(q, k, v, d_o, qt, kt, dot, m, l, delta, dq, dk, dv, nullptr, B, T, Tpad, heads, stream);
 }

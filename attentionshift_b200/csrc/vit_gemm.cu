@@ -61,7 +61,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), e, hx);                            // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
 
-template <int kPair, int kEpi>     // kEpi: epilogue mode, compiled in (keeps the staged epilogue inside the register budget); kPair 2: a pair of CTAs (cluster of 2) drives ONE cta_group::2 MMA of shape 256x256; 1: stand-alone CTA, 128x256
+template <int kPair, int kEpi, bool kTN = false>     // kTN: both operands MN-major (see as_linear_tn_f16); kEpi: epilogue mode, compiled in (keeps the staged epilogue inside the register budget); kPair 2: a pair of CTAs (cluster of 2) drives ONE cta_group::2 MMA of shape 256x256; 1: stand-alone CTA, 128x256
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const GemmParams p) {
@@ -116,7 +116,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles_per_batch = num_mp * num_n;
   const int tiles = tiles_per_batch * p.batch;
-  const int kblocks = p.K / BK;
+  const int kblocks = (p.K + BK - 1) / BK;                  // (K % 64 != 0 only with kTN: TMA zero-fills the missing rows)
 
   if (warp == 0) {
     if (elect_one()) {
@@ -127,7 +127,23 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const int m_blk = kPair * (tb / num_n) + rank, n_blk = tb % num_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (kPair == 2) {
+          if (kTN) {
+            // operands stored [reduction, M] / [reduction, N]: boxes of 64 reduction rows x 64 contiguous M / N elements
+            // (8 KB each, 128-byte swizzle), consumed as MN-major tiles -- no transposed copy of the activations exists
+            if (kPair == 2) { if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + kBBytes)); }
+            else mbar_expect_tx(&full[stage], A_BYTES + kBBytes);
+#pragma unroll
+            for (int h = 0; h < A_BYTES / 8192; ++h) {
+              if (kPair == 2) tma_load_3d_2cta(smem_a + stage * A_BYTES + h * 8192, &tm_a, &full[stage], m_blk * BM + h * 64, kb * BK, bi);
+              else tma_load_3d(smem_a + stage * A_BYTES + h * 8192, &tm_a, &full[stage], m_blk * BM + h * 64, kb * BK, bi);
+            }
+#pragma unroll
+            for (int h = 0; h < kBBytes / 8192; ++h) {
+              const int n0 = n_blk * BN + (kPair == 2 ? rank * (BN / 2) : 0) + h * 64;
+              if (kPair == 2) tma_load_3d_2cta(smem_b + stage * kBBytes + h * 8192, &tm_b, &full[stage], n0, kb * BK, bi);
+              else tma_load_3d(smem_b + stage * kBBytes + h * 8192, &tm_b, &full[stage], n0, kb * BK, bi);
+            }
+          } else if (kPair == 2) {
             if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + kBBytes));     // both CTAs' boxes land on my barrier
             tma_load_3d_2cta(smem_a + stage * A_BYTES, &tm_a, &full[stage], kb * BK, m_blk * BM, bi);
             tma_load_3d_2cta(smem_b + stage * kBBytes, &tm_b, &full[stage], kb * BK, n_blk * BN + rank * (BN / 2), bi);
@@ -143,7 +159,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     }
   } else if (warp == 1) {
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc(0, BM * kPair, BN);
+      constexpr uint32_t idesc = umma_idesc(0, BM * kPair, BN) | (kTN ? (1u << 15) | (1u << 16) : 0u);   // MN-major A and B
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -159,12 +175,11 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             const uint32_t b_base = smem_u32(smem_b + stage * kBBytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              if (kPair == 2)
-                mma_f16_ss_2cta(tmem_base + acc * BN, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32),
-                                idesc, (kb | k) != 0);
-              else
-                mma_f16_ss(tmem_base + acc * BN, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32),
-                           idesc, (kb | k) != 0);
+              // K-major: 16 k = 32 bytes along the row; MN-major: 16 k = two 8-row swizzle atoms (2 KB), 64-element blocks 8 KB apart
+              const uint64_t da = kTN ? umma_desc_mn_sw128(a_base + k * 2048, 8192) : umma_desc_k_sw128(a_base + k * 32);
+              const uint64_t db = kTN ? umma_desc_mn_sw128(b_base + k * 2048, 8192) : umma_desc_k_sw128(b_base + k * 32);
+              if (kPair == 2) mma_f16_ss_2cta(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0);
+              else mma_f16_ss(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0);
             }
             if (kPair == 2) {
               tc_commit_2cta_mcast(&empty[stage], (uint16_t)3);            // frees the stage in both CTAs
@@ -398,6 +413,52 @@ int launch_linear(const void* x, const void* w, long long x_rows_per_batch, long
 }
 
 }  // namespace
+
+// out [M, N] f32 = a^T b for a [R, M], b [R, N] fp16 row-major (R = reduction length, any value; M, N multiples of 64).
+// The weight gradient of a Linear, dW = dY^T X (R = tokens), straight from the row-major activations: the tiles are loaded
+// as 64 x 64 boxes and multiplied as MN-major operands, where the K-major kernel would need both tensors transposed first.
+extern "C" int as_linear_tn_f16(const void* a_f16, const void* b_f16, float* out, int R, int M, int N, cudaStream_t stream) {
+  if (R < 1 || M < 64 || N < 64 || M % 64 || N % 64) return AS_ERR_BAD_ARG;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = R; p.epi = EPI_F32; p.out = out; p.heads = 1; p.batch = 1; p.ldo = N; p.alpha = 1.f;
+  CUtensorMap tm_a, tm_b;
+  uint64_t dims_a[3] = {(uint64_t)M, (uint64_t)R, 1}, str_a[2] = {(uint64_t)M * 2, (uint64_t)R * M * 2};
+  uint64_t dims_b[3] = {(uint64_t)N, (uint64_t)R, 1}, str_b[2] = {(uint64_t)N * 2, (uint64_t)R * N * 2};
+  uint32_t box[3] = {64, 64, 1};
+  int r = as_encode_tmap(&tm_a, a_f16, 2, 3, dims_a, str_a, box);
+  if (!r) r = as_encode_tmap(&tm_b, b_f16, 2, 3, dims_b, str_b, box);
+  if (r) return r;
+  int dev, num_sms;
+  AS_CUDA(cudaGetDevice(&dev));
+  AS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const bool pair = num_m > 1;
+  const void* fn = pair ? (const void*)linear_tcgen05_kernel<2, EPI_F32, true> : (const void*)linear_tcgen05_kernel<1, EPI_F32, true>;
+  static bool attr_done[2] = {};
+  if (!attr_done[pair]) {
+    AS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done[pair] = true;
+  }
+  void* args[] = {(void*)&tm_a, (void*)&tm_b, (void*)&p};
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (!pair) {
+    cfg.gridDim = dim3(num_n < num_sms ? num_n : num_sms);
+  } else {
+    const int tiles = ((num_m + 1) / 2) * num_n, max_clusters = num_sms / 2;
+    cfg.gridDim = dim3(2 * (tiles < max_clusters ? tiles : max_clusters));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  AS_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  AS_LAUNCH_CHECK();
+  return 0;
+}
 
 // mode: 0 = fp16 out, 1 = GELU -> fp16 out, 2 = fp32 out = resid + y, 4 = fp32 out
 extern "C" int as_linear_f16(const void* x_f16, const void* w_f16, const float* bias, void* out, const float* resid,

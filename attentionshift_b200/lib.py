@@ -18,12 +18,20 @@ _vp, _i, _ll, _f, _d, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, c
 # name -> (restype, argtypes); MUST mirror include/attnshift_b200.h (tests/test_abi.py checks the symbol list)
 SIGNATURES = {
     'as_linear_f16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'as_linear_tn_f16': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'as_qkv_proj_f16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_layernorm_f16': (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     'as_patch_im2col_f16': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'as_assemble_tokens': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_bwd': (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp]),
+    'as_mhsa_bwd_ex': (_i, [_vp] * 14 + [_i, _i, _i, _i, _vp]),
+    'as_colsum_workspace': (_sz, [_i]),
+    'as_colsum': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'as_gelu_bwd_f16': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'as_layernorm_bwd_workspace': (_sz, [_i]),
+    'as_layernorm_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    'as_attn_bwd_prep': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'as_transpose_pad_f16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_small': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'as_mhsa_set_variant': (_i, [_i]),

@@ -26,6 +26,17 @@ def linear_f16(x, w, bias=None, mode=EPI_F16, resid=None):
     return out
 
 
+def linear_tn_f16(a, b):
+    """a [R,M], b [R,N] fp16 -> a^T b [M,N] fp32 (the weight gradient dY^T X) without transposed copies of the operands."""
+    L = _l.load()
+    R, M = a.shape
+    N = b.shape[1]
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and b.shape[0] == R
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _l.check(L.as_linear_tn_f16(_l.ptr(a), _l.ptr(b), _l.ptr(out), R, M, N, _l.stream_ptr()), 'as_linear_tn_f16')
+    return out
+
+
 def qkv_proj(x, w, bias, B, T, heads, Tpad):
     """VT:76 qkv Linear + head split.  x [B*T,C] fp16 -> q,k [B,h,T,64] fp16, vT [B,h,64,Tpad] fp16 (zero padded)."""
     L = _l.load()

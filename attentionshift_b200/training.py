@@ -10,11 +10,16 @@ have hand-written backward passes behind ``torch.autograd.Function``:
                      projection's dX / dW GEMMs on the same tcgen05 GEMM kernel.
   * ``LinearFn``     proj / fc1 / fc2: forward, dX and dW all on ``as_linear_f16``.
 
-LayerNorm, GELU and the residual adds stay torch ops (element-wise, autograd's own backward).  Like the reference's AMP path the
+``BlockFn`` (the default of ``block_forward``) makes a whole block one autograd node: LayerNorm backward (with the residual
+gradient folded in), GELU backward + bias gradients, casts and the attention backward's operand preparation run on the kernels
+of ``csrc/vit_train.cu``; only the forward GELU is a torch op.  The per-op functions below remain for the patch embedding and as
+the unfused comparison path (``fused=False``).  Like the reference's AMP path the
 gradients that enter a GEMM are rounded to fp16: callers scale the loss (``apex.amp.scale_loss`` in the reference) when their
 gradients are small.  Layout shuffles between the head-major attention tensors and the token-major GEMM operands (transposes,
 zero padding of the reduction dimension to a multiple of 64) are torch copies.
 """
+import os
+
 import torch
 
 from . import lib as _l
@@ -135,10 +140,154 @@ class AttentionFn(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
-def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None):
-    """VT:109-124 with autograd.  x [B*T, C] fp32 residual stream -> (x, head-mean attention (detached) or None)."""
+_WS = {}
+USE_TN_GEMM = os.environ.get('AS_TRAIN_TN_GEMM', '1') != '0'      # dW GEMMs read the row-major activations directly
+
+
+def _workspace(dev, nbytes):
+    """One scratch buffer per device for the column partials of the reductions below (stream-ordered reuse)."""
+    ws = _WS.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS[dev] = torch.empty(max(int(nbytes), 1 << 24), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def colsum(x, cast=False):
+    """x [M,N] fp32 / fp16 -> column sums [N] fp32 (the bias gradient); ``cast``: also half(x) from the same pass."""
+    L = _l.load()
+    x = x.contiguous()
+    M, N = x.shape
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    x16 = torch.empty(M, N, device=x.device, dtype=torch.float16) if cast else None
+    ws = _workspace(x.device, L.as_colsum_workspace(N))
+    _l.check(L.as_colsum(_l.ptr(x), int(x.dtype == torch.float16), M, N, _l.ptr(x16), _l.ptr(out), _l.ptr(ws), ws.numel(),
+                         _l.stream_ptr()), 'as_colsum')
+    return out, x16
+
+
+def gelu_bwd(d_hid, pre):
+    """d_hid, pre [M,N] fp16 -> (d_pre = d_hid * gelu'(pre) fp16, its column sums fp32)."""
+    L = _l.load()
+    M, N = pre.shape
+    d_pre = torch.empty_like(pre)
+    db = torch.empty(N, device=pre.device, dtype=torch.float32)
+    ws = _workspace(pre.device, L.as_colsum_workspace(N))
+    _l.check(L.as_gelu_bwd_f16(_l.ptr(d_hid.contiguous()), _l.ptr(pre), M, N, _l.ptr(d_pre), _l.ptr(db), _l.ptr(ws), ws.numel(),
+                               _l.stream_ptr()), 'as_gelu_bwd_f16')
+    return d_pre, db
+
+
+def layernorm_bwd(x, gamma, dy16, resid_grad, eps):
+    """Backward of ``ops.layernorm_f16``: -> (dx fp32 [M,C] (+ resid_grad), d gamma, d beta)."""
+    L = _l.load()
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    dgb = torch.empty(2, C, device=x.device, dtype=torch.float32)
+    ws = _workspace(x.device, L.as_layernorm_bwd_workspace(C))
+    _l.check(L.as_layernorm_bwd(_l.ptr(x), _l.ptr(gamma.detach().float().contiguous()), _l.ptr(dy16.contiguous()),
+                                _l.ptr(resid_grad), M, C, float(eps), _l.ptr(dx), _l.ptr(dgb), _l.ptr(ws), ws.numel(),
+                                _l.stream_ptr()), 'as_layernorm_bwd')
+    return dx, dgb[0], dgb[1]
+
+
+def attn_bwd_prep(d_o16, o16, B, T, heads):
+    """d_o, o [B*T, h*64] fp16 -> (d_oh [B,h,T,64] fp16, delta [B,h,T] fp32)."""
+    L = _l.load()
+    d_oh = torch.empty(B, heads, T, 64, device=o16.device, dtype=torch.float16)
+    delta = torch.empty(B, heads, T, device=o16.device, dtype=torch.float32)
+    _l.check(L.as_attn_bwd_prep(_l.ptr(d_o16.contiguous()), _l.ptr(o16), B, T, heads, _l.ptr(d_oh), _l.ptr(delta), _l.stream_ptr()),
+             'as_attn_bwd_prep')
+    return d_oh, delta
+
+
+class BlockFn(torch.autograd.Function):
+    """One pre-LN block (VT:109-124) with a hand-scheduled backward: every pass over a [tokens, C] tensor that autograd would
+    spend on a cast, a bias-gradient reduction, a GELU / LayerNorm backward or a residual-gradient add is folded into one of
+    the kernels of ``csrc/vit_train.cu``; the attention backward writes dQ | dK | dV straight into the qkv Linear's layout.
+    Saved per block: x, x1 (fp32), LN outputs, o, pre, gelu(pre) (fp16), q, k, v^T, (m, l), fp16 weights.
+    -> (x_out [B*T,C] fp32, q, k, m, l); q, k, m, l are not differentiable (they feed the head-mean pass)."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, B, T, heads, eps1, eps2):
+        import torch.nn.functional as F
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()
+        w16 = lambda t: t.detach().half().contiguous()
+        x = x.contiguous()
+        Tpad = (T + 127) // 128 * 128
+        xn1 = ops.layernorm_f16(x, f32(n1w), f32(n1b), eps1)
+        wq, wp, w1, w2 = w16(qkvw), w16(pw), w16(f1w), w16(f2w)
+        q, k, vt = ops.qkv_proj(xn1, wq, f32(qkvb), B, T, heads, Tpad)
+        o, m, l = ops.mhsa_fwd(q, k, vt, T)
+        o = o.view(B * T, -1)
+        x1 = ops.linear_f16(o, wp, f32(pb), ops.EPI_RESID_F32, resid=x)
+        xn2 = ops.layernorm_f16(x1, f32(n2w), f32(n2b), eps2)
+        pre = ops.linear_f16(xn2, w1, f32(f1b), ops.EPI_F16)
+        hid = F.gelu(pre)
+        x2 = ops.linear_f16(hid, w2, f32(f2b), ops.EPI_RESID_F32, resid=x1)
+        ctx.save_for_backward(x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w)
+        ctx.dims = (B, T, heads, eps1, eps2)
+        ctx.has_bias = (qkvb is not None, pb is not None, f1b is not None, f2b is not None)
+        ctx.mark_non_differentiable(q, k, m, l)
+        return x2, q, k, m, l
+
+    @staticmethod
+    def backward(ctx, dy, _dq, _dk, _dm, _dl):
+        x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w = ctx.saved_tensors
+        B, T, heads, eps1, eps2 = ctx.dims
+        need = ctx.needs_input_grad
+        L = _l.load()
+        M, C = x.shape
+        Mp = (M + 63) // 64 * 64
+        Tpad = vt.shape[-1]
+        wt = lambda w: transpose_pad(w, w.shape[0])                       # [N,K] -> [K,N]: operand of dX = dY W
+        if USE_TN_GEMM and C % 64 == 0:
+            dwf = lambda d16, a16: ops.linear_tn_f16(d16.contiguous(), a16.contiguous())                               # dY^T A
+        else:
+            dwf = lambda d16, a16: ops.linear_f16(transpose_pad(d16, Mp), transpose_pad(a16, Mp), None, ops.EPI_F32)
+        dy = dy.contiguous().float()
+        # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(norm2(x1))))
+        db2, dy16 = colsum(dy, cast=True)
+        d_hid = ops.linear_f16(dy16, wt(w2), None, ops.EPI_F16)
+        dw2 = dwf(dy16, hid) if need[11] else None
+        d_pre, db1 = gelu_bwd(d_hid, pre)
+        d_xn2 = ops.linear_f16(d_pre, wt(w1), None, ops.EPI_F16)
+        dw1 = dwf(d_pre, xn2) if need[9] else None
+        dx1, dg2, dbt2 = layernorm_bwd(x1, n2w, d_xn2, dy, eps2)          # + the residual branch's gradient
+        # ---- attention branch: x1 = x + proj(attn(norm1(x)))
+        dbp, dy16 = colsum(dx1, cast=True)
+        d_o = ops.linear_f16(dy16, wt(wp), None, ops.EPI_F16)
+        dwp = dwf(dy16, o) if need[5] else None
+        d_oh, delta = attn_bwd_prep(d_o, o, B, T, heads)
+        v = transpose_pad(vt, 64)[..., :T, :].contiguous()
+        qt, kt, dot = transpose_pad(q, Tpad), transpose_pad(k, Tpad), transpose_pad(d_oh, Tpad)
+        dqkv = torch.empty(M, 3 * C, device=x.device, dtype=torch.float16)
+        _l.check(L.as_mhsa_bwd_ex(_l.ptr(q), _l.ptr(k), _l.ptr(v), _l.ptr(d_oh), _l.ptr(qt), _l.ptr(kt), _l.ptr(dot), _l.ptr(m),
+                                  _l.ptr(l), _l.ptr(delta), None, None, None, _l.ptr(dqkv), B, T, Tpad, heads, _l.stream_ptr()),
+                 'as_mhsa_bwd_ex')
+        dbq, _ = colsum(dqkv)
+        d_xn1 = ops.linear_f16(dqkv, wt(wq), None, ops.EPI_F16)
+        dwq = dwf(dqkv, xn1) if need[3] else None
+        dx0, dg1, dbt1 = layernorm_bwd(x, n1w, d_xn1, dx1, eps1)
+        hb = ctx.has_bias
+        return (dx0, dg1, dbt1, dwq, dbq if hb[0] else None, dwp, dbp if hb[1] else None, dg2, dbt2, dw1, db1 if hb[2] else None,
+                dw2, db2 if hb[3] else None, None, None, None, None, None)
+
+
+def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None, fused=True):
+    """VT:109-124 with autograd.  x [B*T, C] fp32 residual stream -> (x, head-mean attention (detached) or None).
+    ``fused`` (default): the whole block is one autograd node (``BlockFn``); otherwise per-op nodes with torch LayerNorm / GELU."""
     import torch.nn.functional as F
     C = x.shape[1]
+    if fused and C % 128 == 0 and C <= 1024:
+        x2, q, k, m, l = BlockFn.apply(x, blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias,
+                                       blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2.weight, blk.norm2.bias,
+                                       blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias, B, T, heads,
+                                       blk.norm1.eps, blk.norm2.eps)
+        attn = None
+        if want_attn:
+            with torch.no_grad():
+                attn, _ = ops.attn_headmean(q, k, m, l, T, **(headmean_kwargs or {}))
+        return x2, attn
     xn = F.layer_norm(x, (C,), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps).half()
     o, q, k, m, l = AttentionFn.apply(xn, blk.attn.qkv.weight, blk.attn.qkv.bias, B, T, heads)
     attn = None

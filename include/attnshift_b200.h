@@ -39,6 +39,11 @@ typedef struct CUstream_st* as_stream_t; /* == cudaStream_t */
 int as_linear_f16(const void* x_f16, const void* w_f16, const float* bias, void* out, const float* resid, int M, int N,
                   int K, int mode, as_stream_t stream);
 
+/* Weight gradient of a Linear without transposed copies: out [M, N] f32 = a^T b for a [R, M], b [R, N] fp16 row-major
+ * (dW = dY^T X, R = tokens; autograd's addmm of VT:76 / 84 / 52 / 54 in the reference).  Same tcgen05 kernel as as_linear_f16
+ * with both operands consumed as MN-major tiles; R arbitrary (TMA zero-fills), M and N multiples of 64. */
+int as_linear_tn_f16(const void* a_f16, const void* b_f16, float* out, int R, int M, int N, as_stream_t stream);
+
 /* VT:76: qkv Linear fused with the reshape/permute to heads: q,k [B,h,T,64] f16, vt [B,h,64,Tpad] f16 (V transposed). */
 int as_qkv_proj_f16(const void* x_f16, const void* w_f16, const float* bias, void* q, void* k, void* vt, int B, int T,
                     int Tpad, int heads, as_stream_t stream);
@@ -71,6 +76,34 @@ int as_transpose_pad_f16(const void* src, void* dst, int batch, int R, int C, in
 int as_mhsa_bwd(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt, const void* dot,
                 const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv, int B, int T, int Tpad,
                 int heads, as_stream_t stream);
+
+/* as_mhsa_bwd with one more output mode: dqkv16 non-null -> dQ | dK | dV are written as fp16 into ONE [B*T, 3*heads*64]
+ * tensor laid out like the output of VT:76's qkv Linear (column = which*C + head*64 + d), the operand of that Linear's dX /
+ * dW GEMMs; dq / dk / dv are then not written (may be null). */
+int as_mhsa_bwd_ex(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                   const void* dot, const float* m, const float* l, const float* delta, float* dq, float* dk, float* dv,
+                   void* dqkv16, int B, int T, int Tpad, int heads, as_stream_t stream);
+
+/* ---- element-wise / reduction half of the block backward (VT:109-124 under autograd in the reference)
+ * as_colsum: out [N] f32 = column sums of x [M, N] (bias gradient); x fp16 (x_is_f16) or fp32; cast16 (fp32 x only, may be
+ *   null) receives half(x), the operand of the following GEMMs.  N % 4 == 0.
+ * as_gelu_bwd_f16: d_pre [M, N] fp16 = d_hid * gelu'(pre) (erf GELU, VT:40) and d_bias [N] = column sums of d_pre.
+ * as_layernorm_bwd: x [M, C] f32 = the LayerNorm input (statistics are recomputed), dy [M, C] fp16 = gradient of the fp16
+ *   LayerNorm output; dx [M, C] f32 = LayerNorm backward (+ resid_grad [M, C] f32 when non-null: the residual branch of
+ *   VT:113-114); dgb [2, C] = d gamma | d beta.  C a multiple of 128, <= 1024.
+ * as_attn_bwd_prep: d_o, o [B, T, heads*64] fp16 -> d_oh [B, heads, T, 64] (head-major copy of d_o) and
+ *   delta [B, heads, T] = rowsum(d_o o o), the inputs of as_mhsa_bwd.
+ * Workspaces: as_colsum_workspace(N) bytes for as_colsum / as_gelu_bwd_f16, as_layernorm_bwd_workspace(C).  Column partials
+ * are summed in a fixed order (no atomics). */
+size_t as_colsum_workspace(int N);
+int as_colsum(const void* x, int x_is_f16, int M, int N, void* cast16, float* out, void* workspace, size_t workspace_bytes,
+              as_stream_t stream);
+int as_gelu_bwd_f16(const void* d_hid, const void* pre, int M, int N, void* d_pre, float* d_bias, void* workspace,
+                    size_t workspace_bytes, as_stream_t stream);
+size_t as_layernorm_bwd_workspace(int C);
+int as_layernorm_bwd(const float* x, const float* gamma, const void* dy, const float* resid_grad, int M, int C, float eps,
+                     float* dx, float* dgb, void* workspace, size_t workspace_bytes, as_stream_t stream);
+int as_attn_bwd_prep(const void* d_o, const void* o, int B, int T, int heads, void* d_oh, float* delta, as_stream_t stream);
 
 /* VTD:236/242 attn.mean(1): out [B,T,ld] f32 (ld >= T), rowsum_part [B,T,rowsum_slices*ceil(T/128)] partial row sums in
  * column order (may be NULL).  rowsum_slices = 4: persistent schedule (needs ld = T rounded up to 128), one partial per
