@@ -66,6 +66,7 @@ __device__ __forceinline__ bool in_box(const Box& b, int n, int wp) {
 
 struct FusedParams {
   int n_img, N, C, hp, wp, S, G, n_shift, clamp0;
+  int cluster;                 // the G CTAs of an image form one thread-block cluster: group barriers are barrier.cluster
   int blocked;                 // token copies stored as 8 x 8 patch blocks (hp, wp multiples of 8): a 64-token unit is one block
   float tt0, temp;
   const int* img_first; const int* img_nobj; const float* rois;
@@ -100,6 +101,13 @@ __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
     __threadfence();
   }
   __syncthreads();
+}
+// One image = one group of G CTAs.  When the group is a thread-block cluster (G in {2, 4, 8, 16}) the hardware cluster barrier
+// (release / acquire at cluster scope: the partials in global memory written before it are visible to the peers after it)
+// replaces the global counter + polling loop.
+__device__ __forceinline__ void group_sync(int cluster, unsigned* ctr, unsigned target) {
+  if (cluster) { __syncwarp(); cluster_sync_all(); }
+  else group_barrier(ctr, target);
 }
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -334,7 +342,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
     };
     phase_c(false);
     bar_target += p.G;
-    group_barrier(ctr, bar_target);
+    group_sync(p.cluster, ctr, bar_target);
     mark(0);
     const unsigned umask = (unit_act_s[0] ? 1u : 0u) | (unit_act_s[1] ? 2u : 0u) | (unit_act_s[2] ? 4u : 0u) | (unit_act_s[3] ? 8u : 0u);
     auto uact = [&](int u) { return ((umask >> u) & 1u) != 0; };
@@ -468,7 +476,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
       mark(1);
       if (last) break;
       bar_target += p.G;
-      group_barrier(ctr, bar_target);
+      group_sync(p.cluster, ctr, bar_target);
       mark(2);
       // ================================================================ phase A2: per-seed statistics, partial Z
       if (wt >= 0) {
@@ -514,7 +522,7 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
       }
       mark(3);
       bar_target += p.G;
-      group_barrier(ctr, bar_target);
+      group_sync(p.cluster, ctr, bar_target);
       mark(4);
       // ================================================================ phase B: assign + update
       if (warp == 0) {
@@ -652,13 +660,13 @@ mean_shift_fused_kernel(const __grid_constant__ CUtensorMap tm_hi64, const __gri
       }
       mark(6);
       bar_target += p.G;
-      group_barrier(ctr, bar_target);
+      group_sync(p.cluster, ctr, bar_target);
       mark(7);
       // ================================================================ phase C: new prototypes
       phase_c(true);
       mark(8);
       bar_target += p.G;
-      group_barrier(ctr, bar_target);
+      group_sync(p.cluster, ctr, bar_target);
       mark(9);
     }
     __syncthreads();
@@ -685,8 +693,14 @@ extern "C" size_t as_mean_shift_fused_workspace(int n_img, int N, int C) {
 }
 
 static unsigned long long* g_fused_dbg = nullptr;
+static int g_fused_clusters = -1;            // co-resident clusters reported for the last cluster launch (diagnostics)
+#ifndef AS_MS_CLUSTER_DEFAULT
+#define AS_MS_CLUSTER_DEFAULT 0
+#endif
 // profiling aid: device buffer of [grid][16] uint64 that receives the accumulated nanoseconds per phase (null = off)
 extern "C" void as_mean_shift_fused_debug(unsigned long long* buf) { g_fused_dbg = buf; }
+// diagnostics: co-resident clusters the driver reported for the last cluster launch (-1: no cluster launch so far)
+extern "C" int as_mean_shift_fused_occupancy(void) { return g_fused_clusters; }
 
 namespace {
 __global__ void fused_split_tokens(const float* __restrict__ feats, long long fstride, int N, int C, int wp, int blocked,
@@ -783,7 +797,31 @@ extern "C" int as_mean_shift_fused(const float* feats, long long feat_img_stride
   int groups = num_sms / G;
   if (groups > n_img) groups = n_img;
   const int grid = groups * G;
+  // cluster launch when the group size allows it (env AS_MS_CLUSTER=0: global-counter barriers under a cooperative launch)
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("AS_MS_CLUSTER"); use_cluster = e ? atoi(e) : AS_MS_CLUSTER_DEFAULT; }
+  p.cluster = use_cluster && (G == 2 || G == 4 || G == 8 || G == 16);
   void* args[] = {&tm[0], &tm[1], &tm[2], &tm[3], &p};
+  if (p.cluster) {
+    if (G > 8) AS_CUDA(cudaFuncSetAttribute(mean_shift_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FUSED_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)mean_shift_fused_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
+    g_fused_clusters = max_clusters;
+    if (max_clusters >= 1) {
+      // fewer co-resident clusters than images: the images are dealt over the clusters that exist (no inter-cluster dependency)
+      if (max_clusters < groups) { groups = max_clusters; cfg.gridDim = dim3(groups * G); }
+      AS_CUDA(cudaLaunchKernelExC(&cfg, (const void*)mean_shift_fused_kernel, args));
+      AS_LAUNCH_CHECK();
+      return 0;
+    }
+    p.cluster = 0;                               // this GPU cannot place a cluster of G such CTAs: counter barriers
+  }
   AS_CUDA(cudaLaunchCooperativeKernel((const void*)mean_shift_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args, smem, stream));
   AS_LAUNCH_CHECK();
   return 0;

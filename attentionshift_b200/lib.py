@@ -51,6 +51,7 @@ SIGNATURES = {
     'as_mean_shift_tc': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_mean_shift_fused_workspace': (_sz, [_i, _i, _i]),
     'as_mean_shift_fused_debug': (None, [_vp]),
+    'as_mean_shift_fused_occupancy': (_i, []),
     'as_mean_shift_fused': (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _sz, _vp]),
     'as_mean_shift_v2_supported': (_i, [_i, _i, _i, _i]),
     'as_mean_shift_v2_workspace': (_sz, [_i, _i, _i, _i, _i]),

@@ -233,6 +233,9 @@ int as_mean_shift_tc(const float* feats, long long feat_img_stride, int n_img, i
 size_t as_mean_shift_fused_workspace(int n_img, int N, int C);
 /* profiling aid: device buffer [grid][16] of uint64 receiving accumulated ns per phase of the next calls; NULL = off */
 void as_mean_shift_fused_debug(unsigned long long* buf);
+/* diagnostics: thread-block clusters (one per image group) the driver reported as co-resident for the last cluster launch
+ * of the fused kernel (env AS_MS_CLUSTER=1); -1 before any such launch */
+int as_mean_shift_fused_occupancy(void);
 int as_mean_shift_fused(const float* feats, long long feat_img_stride, int n_img, int N, int C, int hp, int wp,
                         const int* obj_img, const int* img_first, const int* img_nobj, int kmax, const float* rois,
                         int n_tot, int S, float* proto, float* sim_out, int n_shift, double tau0, double temp,
