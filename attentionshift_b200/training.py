@@ -21,6 +21,7 @@ zero padding of the reduction dimension to a multiple of 64) are torch copies.
 import os
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import lib as _l
 from . import ops
@@ -84,6 +85,7 @@ class LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x16, weight = ctx.saved_tensors
         dy16 = dy.half().contiguous()
@@ -104,6 +106,7 @@ class LinearResidFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x16, weight = ctx.saved_tensors
         dy16 = dy.half().contiguous()
@@ -128,6 +131,7 @@ class AttentionFn(torch.autograd.Function):
         return o.view(B * T, -1), q, k, m, l
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, d_o, _dq, _dk, _dm, _dl):
         xn16, weight, q, k, vt, o, m, l = ctx.saved_tensors
         B, T, h = ctx.dims
@@ -231,6 +235,7 @@ class BlockFn(torch.autograd.Function):
         return x2, q, k, m, l
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy, _dq, _dk, _dm, _dl):
         x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w = ctx.saved_tensors
         B, T, heads, eps1, eps2 = ctx.dims
