@@ -96,3 +96,22 @@ def test_attach_and_dropin_keep_the_reference_head():
     pickle.dumps(h2.state_dict())
     h2.mil_head.init_weights()
     assert float(h2.mil_head.fc1.bias.detach().abs().max()) == 0.0
+
+
+def test_match_points_host_route_for_host_tensors():
+    """``match_points`` only takes the device solver for predictions that live on the GPU; host tensors (and
+    ``device_matching = False``) go the reference's way -- scipy on the host -- and return what the assigner returns."""
+    import torch
+    from attentionshift_b200 import assigner as A
+    from attentionshift_b200.registry import build_head
+    head = build_head(dict(type='AttnShiftRoIHead', bbox_head=dict(cam_layer=7, seed_thr=0.2, seed_multiple=0.5)))
+    assert head.device_matching is True
+    g = torch.Generator().manual_seed(4)
+    reg, cls = torch.rand(2, 30, 2, generator=g), torch.randn(2, 30, 20, generator=g)
+    pts = [torch.rand(3, 2, generator=g) * 200, torch.rand(1, 2, generator=g) * 200]
+    lab = [torch.randint(0, 20, (3,), generator=g), torch.randint(0, 20, (1,), generator=g)]
+    pos, pgt = head.match_points(reg, cls, pts, lab, [(200, 200)] * 2)
+    for i in range(2):
+        p_ref, g_ref = A.hungarian_point_assign(reg[i], cls[i], pts[i], lab[i], (200, 200))
+        assert torch.equal(pos[i], p_ref) and torch.equal(pgt[i], g_ref)
+        assert pos[i].numel() == pts[i].shape[0] and bool((pos[i][1:] > pos[i][:-1]).all())
