@@ -136,9 +136,9 @@ class VisionTransformerDet(nn.Module):
             raise ValueError('head_dim must be 64 (ViT-S/B/L)')
         if init_values or qk_scale:
             raise ValueError('layer-scale / qk_scale are not part of the hot path (the shipped configs use neither)')
-        # configs/mae/attnshift_voc12aug.py:29 sets drop_path_rate=0.05.  Dropout and stochastic depth are the identity in
-        # inference mode, and this path is the no-grad forward (the attention-shift head consumes detached tensors, DET:77):
-        # the rates are accepted so that the reference configs build unchanged, and are not applied.
+        # configs/mae/attnshift_voc12aug.py:28 sets drop_path_rate=0.05.  Dropout and stochastic depth are the identity in
+        # inference mode (the no-grad forward); the training forward (_forward_train) applies stochastic depth, the dropout
+        # rates (0 in the shipped configs) are accepted so that the reference configs build unchanged and are not applied.
         self.drop_rate, self.attn_drop_rate, self.drop_path_rate = float(drop_rate), float(attn_drop_rate), float(drop_path_rate)
         self.embed_dim = self.num_features = embed_dim
         self.num_heads = num_heads
@@ -327,7 +327,8 @@ class VisionTransformerDet(nn.Module):
     def _forward_train(self, x):
         """Training forward with autograd (``training.py``): the GEMMs and the attention run on the device kernels in both
         directions, LayerNorm / GELU / residual adds are torch ops.  Same return dict; the head-mean maps are detached (the
-        attention-shift head consumes them without gradient, DET:77 / RH:2356).  drop_rate / drop_path_rate are not applied."""
+        attention-shift head consumes them without gradient, DET:77 / RH:2356).  Stochastic depth (``drop_path_rate``, VT:21-29 / 160)
+        is applied per sample and block; ``drop_rate`` / ``attn_drop_rate`` (0 in the shipped configs) are not."""
         from . import training as TR
         B, _, H, W = x.shape
         Hp, Wp = H // self.patch_size, W // self.patch_size
@@ -344,12 +345,15 @@ class VisionTransformerDet(nn.Module):
         first_attn = 0 if self.attn_layers is None else depth - int(self.attn_layers)
         features, attns = [], []
         Tp = self.point_tokens_num
+        # stochastic depth decay rule of VT:160 (CFG:28 drop_path_rate=0.05); dropout (drop_rate, attn_drop_rate: 0 in the
+        # shipped configs) is not implemented
+        dpr = [float(v) for v in torch.linspace(0, self.drop_path_rate, depth)] if self.training else [0.0] * depth
         for i in range(depth):
             want = self.return_attention and i >= first_attn
             kw = None
             if want and self.attn_format == 'rollout':
                 kw = dict(want_transposed=False, row0=T - Tp) if i == depth - 1 else dict(want_map=False)
-            xs, a = TR.block_forward(self.blocks[i], xs, B, T, self.num_heads, want, kw)
+            xs, a = TR.block_forward(self.blocks[i], xs, B, T, self.num_heads, want, kw, drop_path=dpr[i])
             if self.return_attention:
                 attns.append(a)
             if i in self.out_indices:

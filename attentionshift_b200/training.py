@@ -204,6 +204,35 @@ def attn_bwd_prep(d_o16, o16, B, T, heads):
     return d_oh, delta
 
 
+def mhsa_bwd_qkv16(q, k, v, d_oh, qt, kt, dot, m, l, delta, B, T, Tpad, heads):
+    """``as_mhsa_bwd_ex`` in its fp16 mode: dQ | dK | dV as one [B*T, 3*heads*64] fp16 tensor in the layout of the qkv Linear's
+    output (VT:76)."""
+    L = _l.load()
+    dqkv = torch.empty(B * T, 3 * heads * 64, device=q.device, dtype=torch.float16)
+    _l.check(L.as_mhsa_bwd_ex(_l.ptr(q), _l.ptr(k), _l.ptr(v), _l.ptr(d_oh), _l.ptr(qt), _l.ptr(kt), _l.ptr(dot), _l.ptr(m),
+                              _l.ptr(l), _l.ptr(delta), None, None, None, _l.ptr(dqkv), B, T, Tpad, heads, _l.stream_ptr()),
+             'as_mhsa_bwd_ex')
+    return dqkv
+
+
+def drop_path_scale(B, drop_prob, device):
+    """Stochastic depth, VT:21-29: the per-sample factor ``floor(keep + U[0,1)) / keep`` (0 or 1 / keep) of one residual branch."""
+    keep = 1.0 - float(drop_prob)
+    return (keep + torch.rand(B, device=device)).floor_() / keep
+
+
+def _drop_path_apply(x, z, s, B):
+    """x, z = x + branch(x) [B*T, C] fp32 (the GEMM's residual epilogue), s [B] -> x + s_b * branch(x)  (VT:114-115)."""
+    M, C = x.shape
+    return torch.addcmul(x.view(B, -1, C), (z - x).view(B, -1, C), s.view(B, 1, 1)).view(M, C)
+
+
+def _scale_rows(g, s, B):
+    """Gradient of the branch under stochastic depth: rows of sample b times s[b]."""
+    M, C = g.shape
+    return (g.view(B, -1, C) * s.view(B, 1, 1)).view(M, C)
+
+
 class BlockFn(torch.autograd.Function):
     """One pre-LN block (VT:109-124) with a hand-scheduled backward: every pass over a [tokens, C] tensor that autograd would
     spend on a cast, a bias-gradient reduction, a GELU / LayerNorm backward or a residual-gradient add is folded into one of
@@ -212,7 +241,7 @@ class BlockFn(torch.autograd.Function):
     -> (x_out [B*T,C] fp32, q, k, m, l); q, k, m, l are not differentiable (they feed the head-mean pass)."""
 
     @staticmethod
-    def forward(ctx, x, n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, B, T, heads, eps1, eps2):
+    def forward(ctx, x, n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, B, T, heads, eps1, eps2, s1=None, s2=None):
         import torch.nn.functional as F
         f32 = lambda t: None if t is None else t.detach().float().contiguous()
         w16 = lambda t: t.detach().half().contiguous()
@@ -224,11 +253,15 @@ class BlockFn(torch.autograd.Function):
         o, m, l = ops.mhsa_fwd(q, k, vt, T)
         o = o.view(B * T, -1)
         x1 = ops.linear_f16(o, wp, f32(pb), ops.EPI_RESID_F32, resid=x)
+        if s1 is not None:                                                # stochastic depth on the attention branch (VT:114)
+            x1 = _drop_path_apply(x, x1, s1, B)
         xn2 = ops.layernorm_f16(x1, f32(n2w), f32(n2b), eps2)
         pre = ops.linear_f16(xn2, w1, f32(f1b), ops.EPI_F16)
         hid = F.gelu(pre)
         x2 = ops.linear_f16(hid, w2, f32(f2b), ops.EPI_RESID_F32, resid=x1)
-        ctx.save_for_backward(x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w)
+        if s2 is not None:                                                # ... and on the MLP branch (VT:115)
+            x2 = _drop_path_apply(x1, x2, s2, B)
+        ctx.save_for_backward(x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w, s1, s2)
         ctx.dims = (B, T, heads, eps1, eps2)
         ctx.has_bias = (qkvb is not None, pb is not None, f1b is not None, f2b is not None)
         ctx.mark_non_differentiable(q, k, m, l)
@@ -237,10 +270,9 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, _dq, _dk, _dm, _dl):
-        x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w = ctx.saved_tensors
+        x, xn1, q, k, vt, o, m, l, x1, xn2, pre, hid, wq, wp, w1, w2, n1w, n2w, s1, s2 = ctx.saved_tensors
         B, T, heads, eps1, eps2 = ctx.dims
         need = ctx.needs_input_grad
-        L = _l.load()
         M, C = x.shape
         Mp = (M + 63) // 64 * 64
         Tpad = vt.shape[-1]
@@ -251,7 +283,7 @@ class BlockFn(torch.autograd.Function):
             dwf = lambda d16, a16: ops.linear_f16(transpose_pad(d16, Mp), transpose_pad(a16, Mp), None, ops.EPI_F32)
         dy = dy.contiguous().float()
         # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(norm2(x1))))
-        db2, dy16 = colsum(dy, cast=True)
+        db2, dy16 = colsum(dy if s2 is None else _scale_rows(dy, s2, B), cast=True)       # the branch sees s2 * dY, the residual dY
         d_hid = ops.linear_f16(dy16, wt(w2), None, ops.EPI_F16)
         dw2 = dwf(dy16, hid) if need[11] else None
         d_pre, db1 = gelu_bwd(d_hid, pre)
@@ -259,35 +291,35 @@ class BlockFn(torch.autograd.Function):
         dw1 = dwf(d_pre, xn2) if need[9] else None
         dx1, dg2, dbt2 = layernorm_bwd(x1, n2w, d_xn2, dy, eps2)          # + the residual branch's gradient
         # ---- attention branch: x1 = x + proj(attn(norm1(x)))
-        dbp, dy16 = colsum(dx1, cast=True)
+        dbp, dy16 = colsum(dx1 if s1 is None else _scale_rows(dx1, s1, B), cast=True)
         d_o = ops.linear_f16(dy16, wt(wp), None, ops.EPI_F16)
         dwp = dwf(dy16, o) if need[5] else None
         d_oh, delta = attn_bwd_prep(d_o, o, B, T, heads)
         v = transpose_pad(vt, 64)[..., :T, :].contiguous()
         qt, kt, dot = transpose_pad(q, Tpad), transpose_pad(k, Tpad), transpose_pad(d_oh, Tpad)
-        dqkv = torch.empty(M, 3 * C, device=x.device, dtype=torch.float16)
-        _l.check(L.as_mhsa_bwd_ex(_l.ptr(q), _l.ptr(k), _l.ptr(v), _l.ptr(d_oh), _l.ptr(qt), _l.ptr(kt), _l.ptr(dot), _l.ptr(m),
-                                  _l.ptr(l), _l.ptr(delta), None, None, None, _l.ptr(dqkv), B, T, Tpad, heads, _l.stream_ptr()),
-                 'as_mhsa_bwd_ex')
+        dqkv = mhsa_bwd_qkv16(q, k, v, d_oh, qt, kt, dot, m, l, delta, B, T, Tpad, heads)
         dbq, _ = colsum(dqkv)
         d_xn1 = ops.linear_f16(dqkv, wt(wq), None, ops.EPI_F16)
         dwq = dwf(dqkv, xn1) if need[3] else None
         dx0, dg1, dbt1 = layernorm_bwd(x, n1w, d_xn1, dx1, eps1)
         hb = ctx.has_bias
         return (dx0, dg1, dbt1, dwq, dbq if hb[0] else None, dwp, dbp if hb[1] else None, dg2, dbt2, dw1, db1 if hb[2] else None,
-                dw2, db2 if hb[3] else None, None, None, None, None, None)
+                dw2, db2 if hb[3] else None, None, None, None, None, None, None, None)
 
 
-def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None, fused=True):
+def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None, fused=True, drop_path=0.0):
     """VT:109-124 with autograd.  x [B*T, C] fp32 residual stream -> (x, head-mean attention (detached) or None).
     ``fused`` (default): the whole block is one autograd node (``BlockFn``); otherwise per-op nodes with torch LayerNorm / GELU."""
     import torch.nn.functional as F
     C = x.shape[1]
+    s1 = s2 = None
+    if drop_path > 0.0:                       # stochastic depth of the training forward (VT:97, 114-115; CFG:28 drop_path_rate=0.05)
+        s1, s2 = drop_path_scale(B, drop_path, x.device), drop_path_scale(B, drop_path, x.device)
     if fused and C % 128 == 0 and C <= 1024:
         x2, q, k, m, l = BlockFn.apply(x, blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias,
                                        blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2.weight, blk.norm2.bias,
                                        blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias, B, T, heads,
-                                       blk.norm1.eps, blk.norm2.eps)
+                                       blk.norm1.eps, blk.norm2.eps, s1, s2)
         attn = None
         if want_attn:
             with torch.no_grad():
@@ -299,8 +331,10 @@ def block_forward(blk, x, B, T, heads, want_attn, headmean_kwargs=None, fused=Tr
     if want_attn:
         with torch.no_grad():
             attn, _ = ops.attn_headmean(q, k, m, l, T, **(headmean_kwargs or {}))
-    x = LinearResidFn.apply(o, blk.attn.proj.weight, blk.attn.proj.bias, x)
+    z = LinearResidFn.apply(o, blk.attn.proj.weight, blk.attn.proj.bias, x)
+    x = z if s1 is None else _drop_path_apply(x, z, s1, B)
     xn = F.layer_norm(x, (C,), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps).half()
     hid = F.gelu(LinearFn.apply(xn, blk.mlp.fc1.weight, blk.mlp.fc1.bias, False))       # fp16 in / out, fp32 inside
-    x = LinearResidFn.apply(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, x)
+    z = LinearResidFn.apply(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, x)
+    x = z if s2 is None else _drop_path_apply(x, z, s2, B)
     return x, attn
