@@ -55,6 +55,7 @@ def parse():
                     help='forward (default, the BASELINE metric): backbone forward + seed_pseudo_gt; train: + backward of the backbone, '
                          'DDP gradient all-reduce (NCCL) and the optimizer step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-drop-path', action='store_true', help='--mode train: stochastic depth off (the shipped config trains with 0.05)')
     ap.add_argument('--no-reference-config', action='store_true', help='skip the untouched-reference-config leg (cfg2, N=1)')
     ap.add_argument('--small', action='store_true', help='tiny config for a functional check (not a valid bench number)')
     return ap.parse_args()
@@ -186,7 +187,8 @@ def build_models(cfg, dev, reference_config=False):
                                                             cuda_graph=cfg.get('cuda_graph', True))
     bb = build_backbone(dict(type='VisionTransformerDet', img_size=H if H == W else 224, patch_size=16, embed_dim=cfg['embed'],
                              depth=cfg['depth'], num_heads=cfg['heads'], mlp_ratio=4, qkv_bias=True, last_feat=True,
-                             return_attention=True, point_tokens_num=cfg['n_point_tokens'], out_indices=[3, 5, 7, 11], **kw))
+                             return_attention=True, point_tokens_num=cfg['n_point_tokens'], out_indices=[3, 5, 7, 11],
+                             drop_path_rate=cfg.get('drop_path_rate', 0.0), **kw))
     sd = vit_state_dict(cfg['embed'], cfg['depth'], cfg['heads'], H if H == W else 224, n_point_tokens=cfg['n_point_tokens'], seed=0)
     bb.load_state_dict(sd, strict=False)
     bb = bb.to(dev).eval()
@@ -567,6 +569,7 @@ def run_train(args):
     if args.small:
         cfg.update(batch=2, img=(224, 224), depth=7)
     cfg['cuda_graph'] = False
+    cfg['drop_path_rate'] = 0.0 if args.no_drop_path else 0.05     # configs/mae/attnshift_voc12aug.py:28 (stochastic depth in training)
     bb, head = build_models(cfg, dev)
     bb.train()
     model = bb
@@ -624,7 +627,7 @@ def run_train(args):
                                 mode='train: backbone fwd + seed_pseudo_gt (no grad) + surrogate loss + backbone bwd + DDP gradient all-reduce (NCCL, '
                                      '%d parameters = %.0f MB fp32 per step) + fused AdamW' % (n_params, n_params * 4 / 1e6),
                                 collective='torch DDP bucketed all-reduce overlapped with the backward' if world > 1 else 'none (1 rank)',
-                                loss=round(loss, 6)),
+                                drop_path_rate=cfg['drop_path_rate'], loss=round(loss, 6)),
                     clocks=sampler.summary() if sampler is not None else None)
         emit(line)
     if world > 1:
