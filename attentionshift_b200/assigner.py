@@ -49,6 +49,9 @@ def hungarian_point_assign(point_pred, cls_pred, gt_points, gt_labels, img_wh, c
     return pos_inds, assigned[pos_inds] - 1
 
 
+DEVICE_MATCH_MAX = 512          # as_hungarian_points: proposals and GTs per image (shared-memory tables of the solver)
+
+
 def hungarian_point_assign_device(point_pred, cls_pred, gt_points, gt_labels, imgs_wh, cls_weight=1.0, reg_weight=10.0,
                                   want_status=False):
     """The same matching for a whole batch without leaving the device (``as_hungarian_points``: the shortest-augmenting-path

@@ -93,7 +93,9 @@ class AttnShiftRoIHead(nn.Module):
         batch is matched on the device (``as_hungarian_points``, the solver scipy runs, without the reference's ``cost.cpu()``
         round trip); host tensors (or ``device_matching = False``) take the reference's route, scipy on the host."""
         from .assigner import hungarian_point_assign, hungarian_point_assign_device
-        if point_reg.is_cuda and self.device_matching:
+        from .assigner import DEVICE_MATCH_MAX
+        fits = point_reg.shape[1] <= DEVICE_MATCH_MAX and max([int(g.shape[0]) for g in gt_points] + [0]) <= DEVICE_MATCH_MAX
+        if point_reg.is_cuda and self.device_matching and fits:
             return hungarian_point_assign_device(point_reg, point_cls, gt_points, gt_labels, imgs_wh, self.point_cls_weight,
                                                  self.point_reg_weight)
         reg = point_reg.detach().float().cpu()
