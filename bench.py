@@ -432,7 +432,7 @@ def run_ours(args):
         if msf.get('n'):
             ach2 = b_alg / (msf['ms'] / msf['n'] * 1e-3) / 1e9
             what = {'as_mean_shift_v2': 'one persistent cooperative kernel, two CTAs per SM, + the token split kernel',
-                    'as_mean_shift_fused': 'round-1 persistent kernel + the token split kernel',
+                    'as_mean_shift_fused': 'persistent cooperative kernel of round 1 with the round-2 changes (8 x 8 patch-block units, unit skipping) + the token split kernel',
                     'as_mean_shift_tc': '~50 launches', 'as_mean_shift': 'fp32 CUDA-core kernels'}[ms_name]
             traffic2 = None
             t2path = os.path.join(ROOT, 'profiles', {'as_mean_shift_v2': 'ncu_msv2_traffic.json',
